@@ -1,0 +1,310 @@
+// extern "C" surface of the engine (include/pqb200.h): exceptions -> status codes, nothing else.
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "dist.h"
+#include "engine.h"
+
+using pqb::Engine;
+
+struct pqb_sim {
+    Engine* eng;
+    std::string err;
+};
+
+namespace {
+std::string g_create_error;
+
+template <class F>
+int guarded(pqb_sim* s, F&& f) {
+    if (!s || !s->eng) return PQB_ERR_RUNTIME;
+    try {
+        f(*s->eng);
+        return PQB_OK;
+    } catch (const pqb::ValueErr& e) {
+        s->err = e.what();
+        return PQB_ERR_VALUE;
+    } catch (const pqb::CudaErr& e) {
+        s->err = e.what();
+        return PQB_ERR_CUDA;
+    } catch (const pqb::RuntimeErr& e) {
+        s->err = e.what();
+        return PQB_ERR_RUNTIME;
+    } catch (const std::bad_alloc&) {
+        s->err = "out of memory";
+        return PQB_ERR_MEMORY;
+    } catch (const std::invalid_argument& e) {
+        s->err = e.what();
+        return PQB_ERR_VALUE;
+    } catch (const std::exception& e) {
+        s->err = e.what();
+        return PQB_ERR_RUNTIME;
+    }
+}
+
+pqb::TermsView view(const pqb_terms* t, bool cplx) {
+    return pqb::TermsView{t->n_terms, t->term_offsets, t->qubit_index, t->pauli, t->coefficients, cplx};
+}
+}  // namespace
+
+extern "C" {
+
+const char* pqb_version(void) { return "pqb200 0.1 (sm_100a)"; }
+
+int pqb_create(uint32_t seed, const pqb_opts* opts, pqb_sim** out) {
+    if (!out) return PQB_ERR_VALUE;
+    *out = nullptr;
+    pqb_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    try {
+        pqb_sim* s = new pqb_sim{nullptr, {}};
+        try {
+            s->eng = new Engine(seed, o);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+        return PQB_OK;
+    } catch (const pqb::ValueErr& e) {
+        g_create_error = e.what();
+        return PQB_ERR_VALUE;
+    } catch (const pqb::CudaErr& e) {
+        g_create_error = e.what();
+        return PQB_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        g_create_error = "out of memory";
+        return PQB_ERR_MEMORY;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return PQB_ERR_CUDA;
+    }
+}
+
+void pqb_destroy(pqb_sim* sim) {
+    if (!sim) return;
+    delete sim->eng;
+    delete sim;
+}
+
+const char* pqb_last_error(const pqb_sim* sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int pqb_allocate_qubit(pqb_sim* s, uint32_t id) {
+    return guarded(s, [&](Engine& e) { e.allocate_qubit(id); });
+}
+int pqb_deallocate_qubit(pqb_sim* s, uint32_t id) {
+    return guarded(s, [&](Engine& e) { e.deallocate_qubit(id); });
+}
+int pqb_get_classical_value(pqb_sim* s, uint32_t id, double tol, int* out) {
+    return guarded(s, [&](Engine& e) { *out = e.get_classical_value(id, tol) ? 1 : 0; });
+}
+int pqb_is_classical(pqb_sim* s, uint32_t id, double tol, int* out) {
+    return guarded(s, [&](Engine& e) { *out = e.is_classical(id, tol) ? 1 : 0; });
+}
+int pqb_measure_qubits(pqb_sim* s, const uint32_t* ids, size_t n, uint8_t* out) {
+    return guarded(s, [&](Engine& e) { e.measure_qubits(ids, n, out); });
+}
+int pqb_apply_controlled_gate(pqb_sim* s, const double* m, const uint32_t* ids, size_t k, const uint32_t* ctrl,
+                              size_t nc) {
+    return guarded(s, [&](Engine& e) { e.apply_controlled_gate(m, ids, k, ctrl, nc); });
+}
+int pqb_emulate_math_table(pqb_sim* s, const uint64_t* table, size_t table_len, const uint32_t* reg_ids,
+                           const uint32_t* reg_sizes, size_t n_regs, const uint32_t* ctrl, size_t nc) {
+    return guarded(s, [&](Engine& e) {
+        e.emulate_math(pqb::k::MATH_TABLE, 0, 0, table, table_len, reg_ids, reg_sizes, n_regs, ctrl, nc);
+    });
+}
+int pqb_emulate_math_add_constant(pqb_sim* s, int64_t a, const uint32_t* reg_ids, const uint32_t* reg_sizes,
+                                  size_t n_regs, const uint32_t* ctrl, size_t nc) {
+    return guarded(s, [&](Engine& e) {
+        e.emulate_math(pqb::k::MATH_ADD, a, 0, nullptr, 0, reg_ids, reg_sizes, n_regs, ctrl, nc);
+    });
+}
+int pqb_emulate_math_add_constant_mod_n(pqb_sim* s, int64_t a, int64_t N, const uint32_t* reg_ids,
+                                        const uint32_t* reg_sizes, size_t n_regs, const uint32_t* ctrl, size_t nc) {
+    return guarded(s, [&](Engine& e) {
+        e.emulate_math(pqb::k::MATH_ADD_MOD, a, N, nullptr, 0, reg_ids, reg_sizes, n_regs, ctrl, nc);
+    });
+}
+int pqb_emulate_math_multiply_by_constant_mod_n(pqb_sim* s, int64_t a, int64_t N, const uint32_t* reg_ids,
+                                                const uint32_t* reg_sizes, size_t n_regs, const uint32_t* ctrl,
+                                                size_t nc) {
+    return guarded(s, [&](Engine& e) {
+        e.emulate_math(pqb::k::MATH_MUL_MOD, a, N, nullptr, 0, reg_ids, reg_sizes, n_regs, ctrl, nc);
+    });
+}
+int pqb_get_expectation_value(pqb_sim* s, const pqb_terms* t, const uint32_t* ids, size_t n_ids, double* out) {
+    return guarded(s, [&](Engine& e) { *out = e.get_expectation_value(view(t, false), ids, n_ids); });
+}
+int pqb_apply_qubit_operator(pqb_sim* s, const pqb_terms* t, const uint32_t* ids, size_t n_ids) {
+    return guarded(s, [&](Engine& e) { e.apply_qubit_operator(view(t, true), ids, n_ids); });
+}
+int pqb_emulate_time_evolution(pqb_sim* s, const pqb_terms* t, double time, const uint32_t* ids, size_t n_ids,
+                               const uint32_t* ctrl, size_t nc) {
+    return guarded(s, [&](Engine& e) { e.emulate_time_evolution(view(t, false), time, ids, n_ids, ctrl, nc); });
+}
+int pqb_get_probability(pqb_sim* s, const uint8_t* bits, const uint32_t* ids, size_t n, double* out) {
+    return guarded(s, [&](Engine& e) { *out = e.get_probability(bits, ids, n); });
+}
+int pqb_get_amplitude(pqb_sim* s, const uint8_t* bits, const uint32_t* ids, size_t n, double* out) {
+    return guarded(s, [&](Engine& e) {
+        const auto a = e.get_amplitude(bits, ids, n);
+        out[0] = a.real();
+        out[1] = a.imag();
+    });
+}
+int pqb_set_wavefunction(pqb_sim* s, const double* wf, size_t n_amps, const uint32_t* ordering, size_t n) {
+    return guarded(s, [&](Engine& e) { e.set_wavefunction(wf, n_amps, ordering, n); });
+}
+int pqb_collapse_wavefunction(pqb_sim* s, const uint32_t* ids, size_t n_ids, const uint8_t* values, size_t n_values) {
+    return guarded(s, [&](Engine& e) { e.collapse_wavefunction(ids, n_ids, values, n_values); });
+}
+int pqb_run(pqb_sim* s) {
+    return guarded(s, [&](Engine& e) { e.run(); });
+}
+int pqb_num_qubits(pqb_sim* s, size_t* out) {
+    return guarded(s, [&](Engine& e) { *out = e.num_qubits(); });
+}
+int pqb_cheat_map(pqb_sim* s, uint32_t* ids, uint32_t* pos, size_t cap, size_t* out_n) {
+    return guarded(s, [&](Engine& e) { *out_n = e.cheat_map(ids, pos, cap); });
+}
+int pqb_cheat_state(pqb_sim* s, double* out, size_t cap) {
+    return guarded(s, [&](Engine& e) { e.cheat_state(out, cap); });
+}
+int pqb_get_amplitudes(pqb_sim* s, const uint64_t* idx, size_t n, double* out) {
+    return guarded(s, [&](Engine& e) { e.get_amplitudes(idx, n, out); });
+}
+int pqb_apply_gate_stream(pqb_sim* s, const void* packed, size_t n_bytes, size_t n_gates, int fuse) {
+    return guarded(s, [&](Engine& e) { e.apply_gate_stream(packed, n_bytes, n_gates, fuse != 0); });
+}
+int pqb_init_random_state(pqb_sim* s, uint32_t n, uint64_t seed) {
+    return guarded(s, [&](Engine& e) { e.init_random_state(n, seed); });
+}
+int pqb_norm_squared(pqb_sim* s, double* out) {
+    return guarded(s, [&](Engine& e) { *out = e.norm_squared(); });
+}
+int pqb_synchronize(pqb_sim* s) {
+    return guarded(s, [&](Engine& e) { e.synchronize(); });
+}
+int pqb_timer_start(pqb_sim* s) {
+    return guarded(s, [&](Engine& e) { e.timer_start(); });
+}
+int pqb_timer_stop(pqb_sim* s, double* out_ms) {
+    return guarded(s, [&](Engine& e) { *out_ms = e.timer_stop(); });
+}
+int pqb_get_stats(pqb_sim* s, pqb_stats* out) {
+    return guarded(s, [&](Engine& e) { e.get_stats(out); });
+}
+int pqb_reset_stats(pqb_sim* s) {
+    return guarded(s, [&](Engine& e) { e.reset_stats(); });
+}
+int pqb_flush_l2(pqb_sim* s, size_t bytes) {
+    return guarded(s, [&](Engine& e) { e.flush_l2(bytes); });
+}
+int pqb_bench_dense_pass(pqb_sim* s, const double* m, const uint32_t* positions, size_t k, uint64_t ctrl_mask,
+                         int repeats, double* out_ms) {
+    return guarded(s, [&](Engine& e) { *out_ms = e.bench_dense_pass(m, positions, k, ctrl_mask, repeats); });
+}
+int pqb_measure_fp64_peak(pqb_sim* s, double* out) {
+    return guarded(s, [&](Engine& e) { *out = e.measure_fp64_peak(); });
+}
+int pqb_measure_copy_bandwidth(pqb_sim* s, size_t bytes, double* out) {
+    return guarded(s, [&](Engine& e) { *out = e.measure_copy_bandwidth(bytes); });
+}
+
+// ---- host-only helpers ------------------------------------------------------------------------------------------
+int pqb_host_fuse_stream(const void* packed, size_t n_bytes, size_t n_gates, int max_qubits, void* out, size_t out_cap,
+                         size_t* out_bytes, size_t* out_passes) {
+    try {
+        pqb::Fuser fuser;
+        const uint8_t* p = static_cast<const uint8_t*>(packed);
+        const uint8_t* end = p + n_bytes;
+        for (size_t g = 0; g < n_gates; ++g) {
+            if (p + 8 > end) return PQB_ERR_VALUE;
+            uint32_t k, nc;
+            std::memcpy(&k, p, 4);
+            std::memcpy(&nc, p + 4, 4);
+            p += 8;
+            if (k == 0 || k > 5 || nc > 64) return PQB_ERR_VALUE;
+            const size_t d = size_t(1) << k;
+            if (p + 4 * (k + nc) + 16 * d * d > end) return PQB_ERR_VALUE;
+            pqb::Gate gate;
+            gate.targets.resize(k);
+            gate.ctrls.resize(nc);
+            std::memcpy(gate.targets.data(), p, 4 * k);
+            std::memcpy(gate.ctrls.data(), p + 4 * k, 4 * nc);
+            gate.m.resize(d * d);
+            std::memcpy(gate.m.data(), p + 4 * (k + nc), 16 * d * d);
+            p += 4 * (k + nc) + 16 * d * d;
+            fuser.push(std::move(gate));
+        }
+        auto passes = fuser.drain(max_qubits <= 0 ? 5 : max_qubits, [](uint32_t id) { return uint64_t(id); });
+        uint8_t* o = static_cast<uint8_t*>(out);
+        size_t used = 0;
+        for (auto& ps : passes) {
+            const uint32_t k = uint32_t(ps.targets.size()), nc = uint32_t(ps.ctrls.size());
+            const size_t d = size_t(1) << k;
+            const size_t need = 8 + 4 * (k + nc) + 16 * d * d;
+            if (used + need > out_cap) return PQB_ERR_MEMORY;
+            std::memcpy(o + used, &k, 4);
+            std::memcpy(o + used + 4, &nc, 4);
+            std::memcpy(o + used + 8, ps.targets.data(), 4 * k);
+            std::memcpy(o + used + 8 + 4 * k, ps.ctrls.data(), 4 * nc);
+            std::memcpy(o + used + 8 + 4 * (k + nc), ps.m.data(), 16 * d * d);
+            used += need;
+        }
+        if (out_bytes) *out_bytes = used;
+        if (out_passes) *out_passes = passes.size();
+        return PQB_OK;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return PQB_ERR_VALUE;
+    }
+}
+
+int pqb_host_rng_stream(uint32_t seed, size_t n, double* out) {
+    std::mt19937 rng(seed);
+    for (size_t i = 0; i < n; ++i) {
+        const double u0 = double(rng());
+        const double u1 = double(rng());
+        double r = (u0 + u1 * 4294967296.0) / 18446744073709551616.0;
+        if (r >= 1.0) r = std::nextafter(1.0, 0.0);
+        out[i] = r;
+    }
+    return PQB_OK;
+}
+
+int pqb_host_plan_remap(uint8_t* loc, size_t n_logical, int n_local_bits, const uint32_t* need, size_t n_need,
+                        int32_t* out_pairs, size_t cap_pairs, size_t* out_n_pairs) {
+    try {
+        std::vector<uint8_t> l(loc, loc + n_logical);
+        std::vector<uint32_t> nd(need, need + n_need);
+        auto swaps = pqb::plan_remap(l, n_local_bits, nd);
+        if (swaps.size() > cap_pairs) return PQB_ERR_MEMORY;
+        for (size_t i = 0; i < swaps.size(); ++i) {
+            out_pairs[2 * i] = swaps[i].first;
+            out_pairs[2 * i + 1] = swaps[i].second;
+        }
+        std::memcpy(loc, l.data(), n_logical);
+        *out_n_pairs = swaps.size();
+        return PQB_OK;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return PQB_ERR_RUNTIME;
+    }
+}
+
+int pqb_nccl_unique_id(void* out128) {
+    try {
+        pqb::Dist::get_unique_id(out128);
+        return PQB_OK;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return PQB_ERR_CUDA;
+    }
+}
+
+}  // extern "C"

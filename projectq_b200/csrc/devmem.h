@@ -1,0 +1,52 @@
+// Growable device buffer for the state vector.
+//
+// The reference grows the state by allocating a vector of twice the size and copying (reference:
+// simulator.hpp:55-74, with the static tmpBuff1_/tmpBuff2_ recycling at :574-578).  On the GPU the state may use most of
+// the 180 GB of HBM, so a copy-on-grow peak of 1.5x is not affordable: the buffer reserves a virtual address range once
+// and maps physical memory behind it as the state doubles (CUDA virtual memory management), so growing never copies.
+// The driver entry points are fetched through the runtime (cudaGetDriverEntryPoint) so the library does not link
+// libcuda and still loads on a machine without a driver (CPU-side tests of the host logic).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace pqb {
+
+class GrowBuffer {
+public:
+    GrowBuffer() = default;
+    ~GrowBuffer();
+    GrowBuffer(const GrowBuffer&) = delete;
+    GrowBuffer& operator=(const GrowBuffer&) = delete;
+
+    void init(int device);
+    // make at least `bytes` usable; existing contents are preserved; throws std::bad_alloc when the device is full
+    void ensure(size_t bytes);
+    // give physical memory back, keeping at least `bytes` mapped
+    void shrink_to(size_t bytes);
+    void release() { shrink_to(0); }
+
+    void* ptr() const { return reinterpret_cast<void*>(base_); }
+    double2* amps() const { return reinterpret_cast<double2*>(base_); }
+    size_t capacity() const { return mapped_; }
+    bool uses_vmm() const { return vmm_; }
+
+private:
+    struct Chunk {
+        unsigned long long handle;
+        size_t size;
+    };
+    int device_ = 0;
+    bool vmm_ = false;
+    bool inited_ = false;
+    unsigned long long base_ = 0;  // CUdeviceptr
+    size_t va_size_ = 0;
+    size_t mapped_ = 0;
+    size_t gran_ = 0;
+    std::vector<Chunk> chunks_;
+};
+
+}  // namespace pqb

@@ -1,0 +1,228 @@
+// Sharded state communicator — see dist.h.
+#include "dist.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace pqb {
+
+namespace {
+
+struct Nccl {
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+const Nccl& nccl() {
+    static Nccl n = [] {
+        Nccl x;
+        x.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!x.lib) x.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!x.lib) throw std::runtime_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+        auto sym = [&](const char* name) {
+            void* p = dlsym(x.lib, name);
+            if (!p) throw std::runtime_error(std::string("libnccl lacks ") + name);
+            return p;
+        };
+        x.GetUniqueId = reinterpret_cast<decltype(x.GetUniqueId)>(sym("ncclGetUniqueId"));
+        x.CommInitRank = reinterpret_cast<decltype(x.CommInitRank)>(sym("ncclCommInitRank"));
+        x.CommDestroy = reinterpret_cast<decltype(x.CommDestroy)>(sym("ncclCommDestroy"));
+        x.AllReduce = reinterpret_cast<decltype(x.AllReduce)>(sym("ncclAllReduce"));
+        x.Send = reinterpret_cast<decltype(x.Send)>(sym("ncclSend"));
+        x.Recv = reinterpret_cast<decltype(x.Recv)>(sym("ncclRecv"));
+        x.GroupStart = reinterpret_cast<decltype(x.GroupStart)>(sym("ncclGroupStart"));
+        x.GroupEnd = reinterpret_cast<decltype(x.GroupEnd)>(sym("ncclGroupEnd"));
+        x.GetErrorString = reinterpret_cast<decltype(x.GetErrorString)>(sym("ncclGetErrorString"));
+        return x;
+    }();
+    return n;
+}
+
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) throw std::runtime_error(std::string("NCCL error in ") + what + ": " + nccl().GetErrorString(r));
+}
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+}  // namespace
+
+std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_local_bits,
+                                            const std::vector<uint32_t>& need) {
+    std::vector<std::pair<int, int>> swaps;
+    std::vector<uint32_t> global_needed;
+    for (auto lp : need) {
+        if (lp >= loc.size()) throw std::runtime_error("plan_remap: logical position out of range");
+        if (loc[lp] >= 64 && std::find(global_needed.begin(), global_needed.end(), lp) == global_needed.end())
+            global_needed.push_back(lp);
+    }
+    if (global_needed.empty()) return swaps;
+    // owner of each local bit
+    std::vector<int> owner(n_local_bits, -1);
+    for (size_t p = 0; p < loc.size(); ++p)
+        if (loc[p] < 64) owner[loc[p]] = int(p);
+    int b = n_local_bits - 1;
+    for (auto lp : global_needed) {
+        while (b >= 0 && owner[b] >= 0 && std::find(need.begin(), need.end(), uint32_t(owner[b])) != need.end()) --b;
+        if (b < 0) throw std::runtime_error("remap: not enough local qubits to bring every target of the gate on-device");
+        const int r = loc[lp] - 64;
+        swaps.emplace_back(r, b);
+        if (owner[b] >= 0) loc[owner[b]] = uint8_t(64 + r);
+        loc[lp] = uint8_t(b);
+        owner[b] = int(lp);
+        --b;
+    }
+    return swaps;
+}
+
+void Dist::get_unique_id(void* out128) {
+    ncclUniqueId id;
+    nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, sizeof(id));
+}
+
+Dist::Dist(int rank, int world, const void* uid, cudaStream_t stream) : rank_(rank), world_(world), stream_(stream) {
+    g_ = 0;
+    while ((1 << g_) < world_) ++g_;
+    free_mask_ = (uint64_t(1) << g_) - 1;
+    ncclUniqueId id;
+    std::memcpy(&id, uid, sizeof(id));
+    ncclComm_t comm;
+    nccl_check(nccl().CommInitRank(&comm, world_, id, rank_), "ncclCommInitRank");
+    comm_ = comm;
+    ensure_buf(4096);
+}
+
+Dist::~Dist() {
+    if (comm_) nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
+    if (d_buf_) cudaFree(d_buf_);
+}
+
+void Dist::ensure_buf(size_t n) {
+    if (n <= d_buf_doubles_) return;
+    if (d_buf_) {
+        cudaStreamSynchronize(stream_);
+        cudaFree(d_buf_);
+    }
+    cuda_check(cudaMalloc(&d_buf_, n * sizeof(double)), "cudaMalloc(collective staging)");
+    d_buf_doubles_ = n;
+}
+
+int Dist::take_free_rank_bit() {
+    for (int r = 0; r < g_; ++r)
+        if ((free_mask_ >> r) & 1) {
+            free_mask_ &= ~(uint64_t(1) << r);
+            return r;
+        }
+    throw std::logic_error("take_free_rank_bit: none free");
+}
+
+void Dist::reset_rank_bits(int n_used) {
+    free_mask_ = ((uint64_t(1) << g_) - 1) & ~((uint64_t(1) << n_used) - 1);
+}
+
+void Dist::allreduce_sum_vec(double* v, size_t n) {
+    if (n == 0) return;
+    ensure_buf(n);
+    cuda_check(cudaMemcpyAsync(d_buf_, v, n * sizeof(double), cudaMemcpyHostToDevice, stream_), "H2D");
+    nccl_check(nccl().AllReduce(d_buf_, d_buf_, n, ncclDouble, ncclSum, static_cast<ncclComm_t>(comm_), stream_),
+               "ncclAllReduce");
+    cuda_check(cudaMemcpyAsync(v, d_buf_, n * sizeof(double), cudaMemcpyDeviceToHost, stream_), "D2H");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+}
+
+double Dist::allreduce_sum(double v) {
+    allreduce_sum_vec(&v, 1);
+    return v;
+}
+
+unsigned long long Dist::allreduce_min_u64(unsigned long long v) {
+    ensure_buf(1);
+    cuda_check(cudaMemcpyAsync(d_buf_, &v, 8, cudaMemcpyHostToDevice, stream_), "H2D");
+    nccl_check(nccl().AllReduce(d_buf_, d_buf_, 1, ncclUint64, ncclMin, static_cast<ncclComm_t>(comm_), stream_),
+               "ncclAllReduce(min)");
+    cuda_check(cudaMemcpyAsync(&v, d_buf_, 8, cudaMemcpyDeviceToHost, stream_), "D2H");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+    return v;
+}
+
+void Dist::barrier() { allreduce_sum(0.0); }
+
+void Dist::release_rank_bit(int r, bool value, double2* shard, uint64_t n_amps) {
+    if (value) {
+        const int partner = rank_ ^ (1 << r);
+        const bool sender = (rank_ >> r) & 1;
+        ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+        // ranks with the bit set hold the survivors: ship the whole shard to the partner with the bit clear
+        const uint64_t chunk = uint64_t(1) << 26;  // doubles per call stay far below INT_MAX-sized counts
+        for (uint64_t off = 0; off < 2 * n_amps; off += chunk) {
+            const uint64_t cnt = std::min(chunk, 2 * n_amps - off);
+            double* p = reinterpret_cast<double*>(shard) + off;
+            if (sender)
+                nccl_check(nccl().Send(p, cnt, ncclDouble, partner, comm, stream_), "ncclSend");
+            else
+                nccl_check(nccl().Recv(p, cnt, ncclDouble, partner, comm, stream_), "ncclRecv");
+        }
+        if (sender) cuda_check(cudaMemsetAsync(shard, 0, n_amps * sizeof(double2), stream_), "memset");
+    }
+    free_mask_ |= uint64_t(1) << r;
+}
+
+void Dist::swap_bits(int r, int b, double2* shard, int n_local_bits, double2* staging, uint64_t staging_amps,
+                     uint64_t* bytes_sent) {
+    const int partner = rank_ ^ (1 << r);
+    const uint64_t my_bit = (rank_ >> r) & 1;
+    const uint64_t send_bit = 1 - my_bit;  // rank bit 0 ships its local-bit-1 half, rank bit 1 its local-bit-0 half
+    const uint64_t block = uint64_t(1) << b;  // contiguous run inside the half
+    const uint64_t n_blocks = uint64_t(1) << (n_local_bits - 1 - b);
+    ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+    if (staging_amps == 0) throw std::runtime_error("swap_bits: no staging memory");
+    const uint64_t piece = std::min<uint64_t>(block, staging_amps);  // amplitudes per send/recv call
+    // gather as many pieces as fit into the staging area per round, then copy them into place
+    const uint64_t pieces_per_round = std::max<uint64_t>(1, staging_amps / piece);
+    uint64_t in_round = 0;
+    struct Pending {
+        uint64_t off, cnt, soff;
+    };
+    std::vector<Pending> pending;
+    auto flush = [&]() {
+        for (auto& q : pending)
+            cuda_check(cudaMemcpyAsync(shard + q.off, staging + q.soff, q.cnt * sizeof(double2), cudaMemcpyDeviceToDevice,
+                                       stream_),
+                       "staging copy");
+        pending.clear();
+        in_round = 0;
+    };
+    for (uint64_t j = 0; j < n_blocks; ++j) {
+        const uint64_t start = (j << (b + 1)) | (send_bit << b);
+        for (uint64_t o = 0; o < block; o += piece) {
+            const uint64_t cnt = std::min(piece, block - o);
+            const uint64_t soff = in_round * piece;
+            nccl_check(nccl().GroupStart(), "ncclGroupStart");
+            nccl_check(nccl().Send(shard + start + o, 2 * cnt, ncclDouble, partner, comm, stream_), "ncclSend");
+            nccl_check(nccl().Recv(staging + soff, 2 * cnt, ncclDouble, partner, comm, stream_), "ncclRecv");
+            nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+            pending.push_back({start + o, cnt, soff});
+            if (bytes_sent) *bytes_sent += cnt * sizeof(double2);
+            if (++in_round >= pieces_per_round) flush();
+        }
+    }
+    flush();
+}
+
+}  // namespace pqb

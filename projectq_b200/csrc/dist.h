@@ -1,0 +1,56 @@
+// Sharded state across the GPUs of one NVSwitch box: one process per GPU, rank r holds the amplitudes whose rank bits
+// spell r.  The reference has nothing like this (single address space, simulator.hpp:41); this is new work.
+//
+// Only dense gates with a *target* on a rank bit move data: the rank bit is exchanged with a local bit (a global<->local
+// qubit remap), which is a pairwise half-shard exchange over NVLink (ncclSend/ncclRecv).  Controls and diagonal gates on
+// rank bits never communicate.  Scalar results (probabilities, norms, expectation values, measurement bins) are summed
+// with ncclAllReduce.  NCCL is loaded with dlopen so that the library has no link-time dependency on it.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+namespace pqb {
+
+// Pure host logic of a remap, separated so it can be unit-tested without GPUs (pqb_host_plan_remap).
+// loc[p] = placement of logical position p: local bit (< 64) or 64 + rank bit.  `need` lists logical positions that must
+// become local.  Returns the (rank bit, local bit) pairs to exchange, choosing the highest local bits not in `need`
+// (their halves are the largest contiguous blocks), and updates loc.  Throws std::runtime_error if it cannot be done.
+std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_local_bits, const std::vector<uint32_t>& need);
+
+class Dist {
+public:
+    Dist(int rank, int world, const void* nccl_unique_id, cudaStream_t stream);
+    ~Dist();
+
+    int rank_bits() const { return g_; }
+    // rank bits that carry no qubit yet: amplitude is non-zero only on ranks where all of them are 0
+    uint64_t free_rank_bits_mask() const { return free_mask_; }
+    bool has_free_rank_bit() const { return free_mask_ != 0; }
+    int take_free_rank_bit();
+    void reset_rank_bits(int n_used);  // rank bits [0, n_used) carry qubits, the rest are free
+    // the qubit on rank bit r was found classical with `value`: move the surviving shards onto bit r = 0, free the bit
+    void release_rank_bit(int r, bool value, double2* shard, uint64_t n_amps);
+    // exchange rank bit r with local bit b (n_local_bits = log2 n_amps); staging: >= staging_amps device amplitudes
+    void swap_bits(int r, int b, double2* shard, int n_local_bits, double2* staging, uint64_t staging_amps,
+                   uint64_t* bytes_sent);
+
+    double allreduce_sum(double v);
+    void allreduce_sum_vec(double* v, size_t n);  // host vector, in place
+    unsigned long long allreduce_min_u64(unsigned long long v);
+    void barrier();
+
+    static void get_unique_id(void* out128);
+
+private:
+    int rank_, world_, g_;
+    uint64_t free_mask_;
+    cudaStream_t stream_;
+    void* comm_ = nullptr;
+    double* d_buf_ = nullptr;  // device staging for scalar collectives
+    size_t d_buf_doubles_ = 0;
+    void ensure_buf(size_t n);
+};
+
+}  // namespace pqb

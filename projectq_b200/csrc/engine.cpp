@@ -1,0 +1,1082 @@
+// Host controller — see engine.h.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "bits.h"
+#include "dist.h"
+
+namespace pqb {
+
+#define PQB_CHECK(expr)                                                                                       \
+    do {                                                                                                      \
+        cudaError_t err__ = (expr);                                                                           \
+        if (err__ != cudaSuccess)                                                                             \
+            throw CudaErr(std::string("CUDA error: ") + cudaGetErrorString(err__) + " (" #expr ") at " +      \
+                          __FILE__ + ":" + std::to_string(__LINE__));                                         \
+    } while (0)
+
+namespace {
+constexpr size_t kScalarDoubles = 8192;  // device/pinned scalar scratch (bins of the measurement search live here)
+constexpr size_t kMaxPending = 4096;     // gates buffered before the fuser is drained on its own
+constexpr int kBinBits = 10;             // measurement search: logical bits resolved per level
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------------------------------------------
+Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
+    device_ = o.device;
+    fusion_max_ = o.fusion_max_qubits <= 0 ? 5 : std::min(o.fusion_max_qubits, 5);
+    rank_ = o.rank;
+    world_ = o.world_size <= 1 ? 1 : o.world_size;
+    if (world_ & (world_ - 1)) throw ValueErr("pqb_create: world_size must be a power of two");
+    if (rank_ < 0 || rank_ >= world_) throw ValueErr("pqb_create: rank out of range");
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw CudaErr("pqb_create: no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device_ < 0 || device_ >= count) throw CudaErr("pqb_create: CUDA device ordinal out of range");
+    PQB_CHECK(cudaSetDevice(device_));
+    cudaDeviceProp prop;
+    PQB_CHECK(cudaGetDeviceProperties(&prop, device_));
+    sm_count_ = prop.multiProcessorCount;
+    PQB_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    PQB_CHECK(cudaEventCreate(&ev0_));
+    PQB_CHECK(cudaEventCreate(&ev1_));
+    for (auto& b : buf_) b.init(device_);
+    PQB_CHECK(cudaMalloc(&d_partials_, sizeof(double) * k::kReducePartials));
+    PQB_CHECK(cudaMalloc(&d_scalars_, sizeof(double) * kScalarDoubles));
+    PQB_CHECK(cudaMallocHost(&h_pinned_, sizeof(double) * kScalarDoubles));
+
+    if (world_ > 1) {
+        if (!o.nccl_unique_id) throw ValueErr("pqb_create: nccl_unique_id is required when world_size > 1");
+        dist_.reset(new Dist(rank_, world_, o.nccl_unique_id, stream_));
+    }
+
+    // |psi> = 1 on one amplitude (simulator.hpp:48-50).  In a sharded run every rank bit starts free: the single
+    // amplitude lives on rank 0 and the other ranks hold an (identically sized) all-zero shard.
+    try {
+        state_->ensure(std::max<size_t>(sizeof(double2), o.reserve_qubits > 0 && o.reserve_qubits < 40
+                                                             ? (sizeof(double2) << o.reserve_qubits) / size_t(world_)
+                                                             : 0));
+    } catch (const std::bad_alloc&) {
+        throw CudaErr("pqb_create: out of device memory");
+    }
+    const double2 one = make_double2(rank_ == 0 ? 1.0 : 0.0, 0.0);
+    PQB_CHECK(cudaMemcpyAsync(psi(), &one, sizeof(one), cudaMemcpyHostToDevice, stream_));
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+}
+
+Engine::~Engine() {
+    if (stream_) cudaStreamSynchronize(stream_);
+    dist_.reset();
+    if (d_partials_) cudaFree(d_partials_);
+    if (d_scalars_) cudaFree(d_scalars_);
+    if (h_pinned_) cudaFreeHost(h_pinned_);
+    if (d_small_) cudaFree(d_small_);
+    if (d_flush_) cudaFree(d_flush_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    for (auto& b : buf_) b.release();
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+uint32_t Engine::pos_of(uint32_t id, const char* what) const {
+    auto it = map_.find(id);
+    if (it == map_.end()) throw RuntimeErr(std::string(what));
+    return it->second;
+}
+
+bool Engine::layout_is_identity() const {
+    for (int p = 0; p < n_; ++p)
+        if (loc_[p] != p) return false;
+    return true;
+}
+
+uint64_t Engine::logical_to_local_index(uint64_t logical_index, bool* mine) const {
+    uint64_t local = 0;
+    bool ok = true;
+    for (int p = 0; p < n_; ++p) {
+        const uint64_t bit = (logical_index >> p) & 1;
+        if (loc_[p] < 64)
+            local |= bit << loc_[p];
+        else if (uint64_t((rank_ >> (loc_[p] - 64)) & 1) != bit)
+            ok = false;
+    }
+    // free rank bits hold amplitude only where they are 0
+    if (dist_ && (uint64_t(rank_) & dist_->free_rank_bits_mask()) != 0) ok = false;
+    if (mine) *mine = ok;
+    return local;
+}
+
+bool Engine::split_mask(uint64_t lmask, uint64_t lval, uint64_t* local_mask, uint64_t* local_val) const {
+    uint64_t m = 0, v = 0;
+    bool ok = true;
+    for (int p = 0; p < n_; ++p) {
+        if (!((lmask >> p) & 1)) continue;
+        const uint64_t bit = (lval >> p) & 1;
+        if (loc_[p] < 64) {
+            m |= uint64_t(1) << loc_[p];
+            v |= bit << loc_[p];
+        } else if (uint64_t((rank_ >> (loc_[p] - 64)) & 1) != bit)
+            ok = false;
+    }
+    *local_mask = m;
+    *local_val = v;
+    return ok;
+}
+
+double Engine::read_scalar(const double* d_ptr) {
+    PQB_CHECK(cudaMemcpyAsync(h_pinned_, d_ptr, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+    return h_pinned_[0];
+}
+
+double Engine::allreduce_sum(double v) { return dist_ ? dist_->allreduce_sum(v) : v; }
+
+void Engine::ensure_scratch(GrowBuffer& b, size_t bytes) {
+    try {
+        b.ensure(bytes);
+    } catch (const std::bad_alloc&) {
+        throw CudaErr("out of device memory for a scratch copy of the state (" + std::to_string(bytes >> 20) + " MiB)");
+    }
+}
+
+void* Engine::small_upload(const void* src, size_t bytes) {
+    if (bytes > d_small_cap_) {
+        PQB_CHECK(cudaStreamSynchronize(stream_));
+        if (d_small_) cudaFree(d_small_);
+        d_small_cap_ = std::max<size_t>(bytes * 2, 1 << 16);
+        PQB_CHECK(cudaMalloc(&d_small_, d_small_cap_));
+    }
+    // pageable source: the copy is staged by the runtime before the call returns
+    PQB_CHECK(cudaMemcpyAsync(d_small_, src, bytes, cudaMemcpyHostToDevice, stream_));
+    return d_small_;
+}
+
+double Engine::draw_uniform() {
+    // std::uniform_real_distribution<double>(0,1) on std::mt19937 (reference: simulator.hpp:51-52,153) is
+    // generate_canonical<double,53>: two 32-bit draws, low word first (libstdc++ bits/random.tcc).
+    const double u0 = double(rng_());
+    const double u1 = double(rng_());
+    double r = (u0 + u1 * 4294967296.0) / 18446744073709551616.0;
+    if (r >= 1.0) r = std::nextafter(1.0, 0.0);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// allocation
+// ---------------------------------------------------------------------------------------------------------------
+void Engine::allocate_qubit(uint32_t id) {
+    if (known(id)) throw RuntimeErr("AllocateQubit: ID already exists. Qubit IDs should be unique.");
+    if (n_ >= 62) throw RuntimeErr("AllocateQubit: too many qubits");
+    // pending gates keep their meaning: the new qubit is a new most-significant logical bit (simulator.hpp:57)
+    if (dist_ && dist_->has_free_rank_bit()) {
+        // a free rank bit is all-zero outside value 0, which is exactly a fresh |0> qubit: no data moves
+        const int r = dist_->take_free_rank_bit();
+        loc_.push_back(uint8_t(64 + r));
+    } else {
+        const size_t old_bytes = sizeof(double2) << L_;
+        try {
+            state_->ensure(old_bytes * 2);
+        } catch (const std::bad_alloc&) {
+            // give the scratch copies back and retry once
+            scratch1_->release();
+            scratch2_->release();
+            try {
+                state_->ensure(old_bytes * 2);
+            } catch (const std::bad_alloc&) {
+                throw CudaErr("AllocateQubit: out of device memory at " + std::to_string(n_ + 1) + " qubits");
+            }
+        }
+        PQB_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(state_->ptr()) + old_bytes, 0, old_bytes, stream_));
+        loc_.push_back(uint8_t(L_));
+        ++L_;
+    }
+    map_[id] = uint32_t(n_);
+    ++n_;
+}
+
+bool Engine::is_classical(uint32_t id, double tol) {
+    run();
+    const uint32_t lp = pos_of(id, "is_classical(): Unknown qubit id.");
+    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(d_scalars_);
+    std::vector<uint8_t> phys2log;
+    const bool ident = layout_is_identity() && !dist_;
+    uint64_t rank_bits = 0;
+    if (!ident) {
+        phys2log.assign(64, 0);
+        for (int p = 0; p < n_; ++p) phys2log[loc_[p] < 64 ? loc_[p] : L_ + (loc_[p] - 64)] = uint8_t(p);
+        rank_bits = uint64_t(rank_) << L_;
+    }
+    // In a sharded run physical bit L_+r is rank bit r; free rank bits carry no logical qubit, and ranks with such a
+    // bit set hold only zeros, so whatever phys2log says for them is never used.
+    k::classical_probe(ctx(), psi(), local_amps(), loc_[lp] < 64 ? loc_[lp] : L_ + (loc_[lp] - 64), int(lp), tol,
+                       ident ? nullptr : phys2log.data(), dist_ ? L_ + dist_->rank_bits() : n_, rank_bits, d_out);
+    PQB_CHECK(cudaMemcpyAsync(h_pinned_, d_out, 16, cudaMemcpyDeviceToHost, stream_));
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+    unsigned long long m[2];
+    std::memcpy(m, h_pinned_, 16);
+    if (dist_) {
+        m[0] = dist_->allreduce_min_u64(m[0]);
+        m[1] = dist_->allreduce_min_u64(m[1]);
+    }
+    last_probe_[0] = m[0];
+    last_probe_[1] = m[1];
+    const bool down = m[0] != ~0ULL, up = m[1] != ~0ULL;
+    return down != up;
+}
+
+bool Engine::get_classical_value(uint32_t id, double tol) {
+    // first amplitude above tol in the reference's scan order decides (simulator.hpp:81-88): the bit-0 member of a
+    // pair is looked at before its bit-1 partner, so bit 1 wins only with a strictly smaller pair number
+    is_classical(id, tol);
+    return last_probe_[1] < last_probe_[0];
+}
+
+void Engine::deallocate_qubit(uint32_t id) {
+    run();
+    if (!known(id)) throw RuntimeErr("DeallocateQubit: Unknown qubit id.");
+    if (!is_classical(id, 1e-12))
+        throw RuntimeErr(
+            "Error: Qubit has not been measured / uncomputed! There is most likely a bug in your code.");
+    const bool value = last_probe_[1] < last_probe_[0];
+    const uint32_t lp = map_[id];
+    if (!is_local(lp)) {
+        // the qubit sits on a rank bit: hand the bit back, moving the surviving half onto the ranks where it is 0
+        dist_->release_rank_bit(loc_[lp] - 64, value, psi(), local_amps());
+    } else {
+        const int pb = loc_[lp];
+        const uint64_t half = local_amps() >> 1;
+        if (pb == L_ - 1) {
+            // top local bit: the surviving half is contiguous
+            if (value)
+                PQB_CHECK(cudaMemcpyAsync(psi(), psi() + half, half * sizeof(double2), cudaMemcpyDeviceToDevice, stream_));
+        } else {
+            ensure_scratch(*scratch1_, half * sizeof(double2));
+            k::compact_bit(ctx(), psi(), scratch1_->amps(), half, pb, value ? 1 : 0);
+            std::swap(state_, scratch1_);
+        }
+        for (auto& l : loc_)
+            if (l < 64 && l > pb) --l;
+        --L_;
+    }
+    // logical bookkeeping (simulator.hpp:136-141)
+    loc_.erase(loc_.begin() + lp);
+    for (auto& kv : map_)
+        if (kv.second > lp) --kv.second;
+    map_.erase(id);
+    --n_;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gates
+// ---------------------------------------------------------------------------------------------------------------
+void Engine::apply_controlled_gate(const double* m, const uint32_t* ids, size_t k, const uint32_t* ctrl, size_t nc) {
+    if (k > size_t(k::kMaxDense)) throw ValueErr("Gates with more than 5 qubits are not supported!");
+    if (k == 0) throw ValueErr("apply_controlled_gate(): no target qubits");
+    Gate g;
+    g.targets.assign(ids, ids + k);
+    g.ctrls.assign(ctrl, ctrl + nc);
+    for (size_t i = 0; i < k; ++i) {
+        for (size_t j = i + 1; j < k; ++j)
+            if (ids[i] == ids[j]) throw ValueErr("apply_controlled_gate(): duplicate target qubit");
+        for (size_t j = 0; j < nc; ++j)
+            if (ids[i] == ctrl[j]) throw ValueErr("apply_controlled_gate(): a qubit is both target and control");
+    }
+    const size_t d = size_t(1) << k;
+    g.m.resize(d * d);
+    for (size_t i = 0; i < d * d; ++i) g.m[i] = cplx(m[2 * i], m[2 * i + 1]);
+    fuser_.push(std::move(g));
+    ++stats_.gates_ingested;
+    if (fuser_.pending() >= kMaxPending) run();
+}
+
+void Engine::apply_pass(const FusedPass& p) {
+    const int kq = int(p.targets.size());
+    if (kq > k::kMaxDense) throw ValueErr("Gates with more than 5 qubits are not supported!");
+    uint8_t cpos[64];
+    // controls on rank bits switch whole ranks on or off; controls on local bits become the kernel's control mask
+    int ncl = 0;
+    bool active = true;
+    for (auto c : p.ctrls) {
+        const uint32_t lp = map_.at(c);
+        if (is_local(lp))
+            cpos[ncl++] = loc_[lp];
+        else if (!((rank_ >> (loc_[lp] - 64)) & 1))
+            active = false;
+    }
+    if (dist_ && (uint64_t(rank_) & dist_->free_rank_bits_mask()) != 0) active = false;  // all-zero shard
+    std::sort(cpos, cpos + ncl);
+    const size_t D = size_t(1) << kq;
+    if (p.diagonal) {
+        // a diagonal pass needs no remap: targets on rank bits just select a slice of the diagonal for this rank
+        ++stats_.diag_passes;
+        if (!active) return;
+        uint8_t tl[8];
+        int which[8], kl = 0;
+        size_t fixed = 0;
+        for (int l = 0; l < kq; ++l) {
+            const uint32_t lp = map_.at(p.targets[l]);
+            if (is_local(lp)) {
+                tl[kl] = loc_[lp];
+                which[kl++] = l;
+            } else if ((rank_ >> (loc_[lp] - 64)) & 1)
+                fixed |= size_t(1) << l;
+        }
+        double d[64];
+        for (size_t v = 0; v < (size_t(1) << kl); ++v) {
+            size_t idx = fixed;
+            for (int j = 0; j < kl; ++j)
+                if ((v >> j) & 1) idx |= size_t(1) << which[j];
+            d[2 * v] = p.m[idx * D + idx].real();
+            d[2 * v + 1] = p.m[idx * D + idx].imag();
+        }
+        k::apply_diagonal(ctx(), psi(), L_, kl, tl, ncl, cpos, d);
+        return;
+    }
+    ++stats_.dense_passes[kq];
+    if (!active) return;
+    uint8_t tpos[8];
+    for (int l = 0; l < kq; ++l) {
+        const uint32_t lp = map_.at(p.targets[l]);
+        if (!is_local(lp)) throw RuntimeErr("internal: dense target on a rank bit was not remapped");
+        tpos[l] = loc_[lp];
+        if (l > 0 && tpos[l] <= tpos[l - 1]) throw RuntimeErr("internal: pass targets are not in ascending bit order");
+    }
+    k::apply_dense(ctx(), psi(), L_, kq, tpos, ncl, cpos, reinterpret_cast<const double*>(p.m.data()));
+}
+
+// bring the given logical positions onto local bits (global<->local qubit remap over NVLink)
+void Engine::make_local(const std::vector<uint32_t>& need) {
+    if (!dist_) return;
+    bool any = false;
+    for (auto lp : need)
+        if (!is_local(lp)) any = true;
+    if (!any) return;
+    std::vector<std::pair<int, int>> swaps;
+    try {
+        swaps = plan_remap(loc_, L_, need);
+    } catch (const std::runtime_error& e) {
+        throw RuntimeErr(e.what());
+    }
+    // staging: a bounded slice of the second scratch buffer (the state itself may fill most of HBM)
+    const uint64_t want = std::min<uint64_t>(local_amps() >> 1, uint64_t(1) << 26);  // <= 1 GiB
+    ensure_scratch(*scratch2_, std::max<uint64_t>(want, 1) * sizeof(double2));
+    cudaEvent_t e0, e1;
+    PQB_CHECK(cudaEventCreate(&e0));
+    PQB_CHECK(cudaEventCreate(&e1));
+    PQB_CHECK(cudaEventRecord(e0, stream_));
+    for (auto& sw : swaps) {
+        try {
+            dist_->swap_bits(sw.first, sw.second, psi(), L_, scratch2_->amps(), std::max<uint64_t>(want, 1),
+                             &stats_.remap_bytes_sent);
+        } catch (const std::runtime_error& e) {
+            throw CudaErr(e.what());
+        }
+        ++stats_.remaps;
+    }
+    PQB_CHECK(cudaEventRecord(e1, stream_));
+    PQB_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    stats_.remap_ms += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+}
+
+void Engine::run() {
+    if (fuser_.pending() == 0) return;
+    // every id must be known before positions are resolved (the reference would silently insert into map_)
+    // sort key of a qubit inside a pass = its physical place; rank bits sort above all local bits
+    auto key = [this](uint32_t id) -> uint64_t {
+        auto it = map_.find(id);
+        if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
+        return loc_[it->second];
+    };
+    std::vector<FusedPass> passes;
+    try {
+        passes = fuser_.drain(fusion_max_, key);
+    } catch (...) {
+        fuser_.clear();  // never leave a poisoned queue behind (the reference does, simulator.hpp:522-526)
+        throw;
+    }
+    for (auto& p : passes) {
+        if (dist_) {
+            std::vector<uint32_t> need;
+            if (!p.diagonal)
+                for (auto t : p.targets) need.push_back(map_.at(t));
+            make_local(need);
+            // the remap may have moved targets: put the matrix bits back in ascending physical order
+            if (!p.diagonal) Fuser::reorder(p, key);
+        }
+        apply_pass(p);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------------------------------------------
+void Engine::measure_qubits(const uint32_t* ids, size_t n, uint8_t* out) {
+    run();
+    std::vector<uint32_t> lpos(n);
+    for (size_t i = 0; i < n; ++i) lpos[i] = pos_of(ids[i], "measure_qubits(): Unknown qubit id.");
+    const double rnd = draw_uniform();
+
+    // Inverse-CDF search in *logical* index order (simulator.hpp:156-160), kBinBits logical bits per level from the top:
+    // each level sums |psi|^2 over the 2^m bins of the next m logical bits inside the prefix chosen so far, the host
+    // walks the bins sequentially exactly like the reference walks amplitudes, and the search descends into the bin.
+    uint64_t pick = 0;       // logical index bits decided so far (in place)
+    uint64_t decided = 0;    // mask of decided logical bits
+    double remaining = rnd;  // rnd minus the mass of everything before the chosen prefix
+    bool overflowed = false; // the running sum never reached rnd: the reference ends on the last index
+    int top = n_;
+    if (n_ == 0) top = 0;
+    while (top > 0) {
+        const int m = std::min(kBinBits, top);
+        const int lo = top - m;  // bins are logical bits [lo, top)
+        const int n_bins = 1 << m;
+        // local view: decided bits and bin bits that live on local physical bits
+        std::vector<uint8_t> ins;
+        uint8_t bin_pos[16];
+        int m_local = 0;
+        uint64_t fixed_val = 0;
+        bool rank_matches_prefix = true;
+        int bin_is_local[16];
+        for (int b = 0; b < m; ++b) {
+            const int lp = lo + b;
+            bin_is_local[b] = is_local(lp);
+            if (bin_is_local[b]) {
+                bin_pos[m_local++] = loc_[lp];
+                ins.push_back(loc_[lp]);
+            }
+        }
+        for (int lp = top; lp < n_; ++lp) {
+            const uint64_t bit = (pick >> lp) & 1;
+            if (is_local(lp)) {
+                ins.push_back(loc_[lp]);
+                fixed_val |= bit << loc_[lp];
+            } else if (uint64_t((rank_ >> (loc_[lp] - 64)) & 1) != bit)
+                rank_matches_prefix = false;
+        }
+        if (dist_ && (uint64_t(rank_) & dist_->free_rank_bits_mask()) != 0) rank_matches_prefix = false;
+        std::sort(ins.begin(), ins.end());
+        std::vector<double> bins(n_bins, 0.0);
+        if (rank_matches_prefix) {
+            k::bin_sums(ctx(), psi(), L_, int(ins.size()), ins.data(), fixed_val, m_local, bin_pos, d_partials_, d_scalars_);
+            PQB_CHECK(cudaMemcpyAsync(h_pinned_, d_scalars_, sizeof(double) << m_local, cudaMemcpyDeviceToHost, stream_));
+            PQB_CHECK(cudaStreamSynchronize(stream_));
+            // scatter the local bins into the full bin array (rank bits of this rank fill the non-local bin bits)
+            for (int lb = 0; lb < (1 << m_local); ++lb) {
+                int full = 0, j = 0;
+                for (int b = 0; b < m; ++b) {
+                    int bit;
+                    if (bin_is_local[b])
+                        bit = (lb >> j++) & 1;
+                    else
+                        bit = (rank_ >> (loc_[lo + b] - 64)) & 1;
+                    full |= bit << b;
+                }
+                bins[full] = h_pinned_[lb];
+            }
+        }
+        if (dist_) dist_->allreduce_sum_vec(bins.data(), n_bins);
+        // sequential walk (while (P < rnd && pick < size) P += ...; pick--)
+        int chosen = -1;
+        double before = 0.0;
+        if (!overflowed) {
+            double P = 0.0;
+            for (int b = 0; b < n_bins; ++b) {
+                if (P + bins[b] >= remaining && (bins[b] > 0.0 || remaining <= P)) {
+                    chosen = b;
+                    before = P;
+                    break;
+                }
+                P += bins[b];
+            }
+        }
+        if (chosen < 0) {
+            // not reached: at the top level this is the reference's "last index" rule; below it, it can only be a
+            // rounding difference between two summation orders -> stay on the last amplitude that carries weight
+            chosen = n_bins - 1;
+            if (top != n_ || overflowed) {
+                for (int b = n_bins - 1; b >= 0; --b)
+                    if (bins[b] > 0.0) {
+                        chosen = b;
+                        break;
+                    }
+            }
+            overflowed = true;
+        }
+        remaining -= before;
+        pick |= uint64_t(chosen) << lo;
+        decided |= ((uint64_t(1) << m) - 1) << lo;
+        top = lo;
+    }
+    (void)decided;
+
+    uint64_t mask = 0, val = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t bit = (pick >> lpos[i]) & 1;
+        out[i] = uint8_t(bit);
+        mask |= uint64_t(1) << lpos[i];
+        val |= bit << lpos[i];
+    }
+    // zero the amplitudes that disagree, renormalise the rest (simulator.hpp:172-185)
+    uint64_t lmask, lval;
+    const bool mine = split_mask(mask, val, &lmask, &lval);
+    double kept = 0.0;
+    if (mine) {
+        k::norm_masked(ctx(), psi(), local_amps(), lmask, lval, d_partials_, d_scalars_);
+        kept = read_scalar(d_scalars_);
+    }
+    kept = allreduce_sum(kept);
+    const double scale = 1.0 / std::sqrt(kept);
+    if (mine)
+        k::collapse_scale(ctx(), psi(), local_amps(), lmask, lval, scale);
+    else
+        PQB_CHECK(cudaMemsetAsync(psi(), 0, local_amps() * sizeof(double2), stream_));
+}
+
+void Engine::collapse_wavefunction(const uint32_t* ids, size_t n_ids, const uint8_t* values, size_t n_values) {
+    run();
+    if (n_ids != n_values) throw ValueErr("collapse_wavefunction(): ids and values size mismatch");
+    uint64_t mask = 0, val = 0;
+    for (size_t i = 0; i < n_ids; ++i) {
+        const uint32_t lp = pos_of(ids[i],
+                                   "collapse_wavefunction(): Unknown qubit id(s) provided. Try calling eng.flush() before "
+                                   "invoking this function.");
+        mask |= uint64_t(1) << lp;
+        val |= uint64_t(values[i] ? 1 : 0) << lp;
+    }
+    uint64_t lmask, lval;
+    const bool mine = split_mask(mask, val, &lmask, &lval);
+    double prob = 0.0;
+    if (mine) {
+        k::norm_masked(ctx(), psi(), local_amps(), lmask, lval, d_partials_, d_scalars_);
+        prob = read_scalar(d_scalars_);
+    }
+    prob = allreduce_sum(prob);
+    if (prob < 1e-12) throw RuntimeErr("collapse_wavefunction(): Invalid collapse! Probability is ~0.");
+    const double scale = 1.0 / std::sqrt(prob);
+    if (mine)
+        k::collapse_scale(ctx(), psi(), local_amps(), lmask, lval, scale);
+    else
+        PQB_CHECK(cudaMemsetAsync(psi(), 0, local_amps() * sizeof(double2), stream_));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// queries
+// ---------------------------------------------------------------------------------------------------------------
+double Engine::get_probability(const uint8_t* bits, const uint32_t* ids, size_t n) {
+    run();
+    uint64_t mask = 0, val = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t lp =
+            pos_of(ids[i], "get_probability(): Unknown qubit id. Please make sure you have called eng.flush().");
+        mask |= uint64_t(1) << lp;
+        val |= uint64_t(bits[i] ? 1 : 0) << lp;
+    }
+    uint64_t lmask, lval;
+    double p = 0.0;
+    if (split_mask(mask, val, &lmask, &lval)) {
+        k::norm_masked(ctx(), psi(), local_amps(), lmask, lval, d_partials_, d_scalars_);
+        p = read_scalar(d_scalars_);
+    }
+    return allreduce_sum(p);
+}
+
+double Engine::norm_squared() {
+    run();
+    k::norm_masked(ctx(), psi(), local_amps(), 0, 0, d_partials_, d_scalars_);
+    return allreduce_sum(read_scalar(d_scalars_));
+}
+
+std::complex<double> Engine::get_amplitude(const uint8_t* bits, const uint32_t* ids, size_t n) {
+    run();
+    uint64_t chk = 0, index = 0;
+    for (size_t i = 0; i < n; ++i) {
+        auto it = map_.find(ids[i]);
+        if (it == map_.end()) break;
+        chk |= uint64_t(1) << it->second;
+        index |= uint64_t(bits[i] ? 1 : 0) << it->second;
+    }
+    if (chk + 1 != (uint64_t(1) << n_))
+        throw RuntimeErr(
+            "The second argument to get_amplitude() must be a permutation of all allocated qubits. Please make sure you "
+            "have called eng.flush().");
+    double out[2];
+    get_amplitudes(&index, 1, out);
+    return {out[0], out[1]};
+}
+
+void Engine::get_amplitudes(const uint64_t* logical_idx, size_t n, double* out) {
+    run();
+    if (n == 0) return;
+    std::vector<uint64_t> local(n);
+    std::vector<char> mine(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (n_ < 64 && (logical_idx[i] >> n_) != 0) throw ValueErr("get_amplitudes(): index out of range");
+        bool ok;
+        local[i] = logical_to_local_index(logical_idx[i], &ok);
+        mine[i] = ok;
+    }
+    std::vector<uint64_t> staged(3 * n, 0);  // n indices followed by room for n amplitudes
+    std::copy(local.begin(), local.end(), staged.begin());
+    uint64_t* d_idx = static_cast<uint64_t*>(small_upload(staged.data(), staged.size() * sizeof(uint64_t)));
+    double2* d_out = reinterpret_cast<double2*>(d_idx + n);
+    k::gather_indices(ctx(), psi(), d_idx, n, d_out);
+    PQB_CHECK(cudaMemcpyAsync(out, d_out, n * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+    if (dist_) {
+        for (size_t i = 0; i < n; ++i)
+            if (!mine[i]) out[2 * i] = out[2 * i + 1] = 0.0;
+        dist_->allreduce_sum_vec(out, 2 * n);
+    }
+}
+
+void Engine::set_wavefunction(const double* wf, size_t n_amps, const uint32_t* ordering, size_t n) {
+    run();
+    bool ok = map_.size() == n;
+    for (size_t i = 0; ok && i < n; ++i) ok = known(ordering[i]);
+    if (!ok)
+        throw RuntimeErr(
+            "set_wavefunction(): Invalid mapping provided. Please make sure all qubits have been allocated previously "
+            "(call eng.flush()).");
+    if (n_amps != (size_t(1) << n)) throw ValueErr("set_wavefunction(): the wavefunction must have 2^n amplitudes");
+    for (size_t i = 0; i < n; ++i) map_[ordering[i]] = uint32_t(i);
+    if (map_.size() != n) throw RuntimeErr("set_wavefunction(): Invalid mapping provided (duplicate qubit ids).");
+    if (!dist_) {
+        for (int p = 0; p < n_; ++p) loc_[p] = uint8_t(p);
+        PQB_CHECK(cudaMemcpyAsync(psi(), wf, n_amps * sizeof(double2), cudaMemcpyHostToDevice, stream_));
+        PQB_CHECK(cudaStreamSynchronize(stream_));
+        return;
+    }
+    // sharded: logical bits [0, L_) local, the rest on rank bits in order; every rank copies its slice
+    dist_->reset_rank_bits(n_ - L_);
+    for (int p = 0; p < n_; ++p) loc_[p] = uint8_t(p < L_ ? p : 64 + (p - L_));
+    const uint64_t active_ranks = uint64_t(1) << (n_ - L_);
+    if (uint64_t(rank_) < active_ranks)
+        PQB_CHECK(cudaMemcpyAsync(psi(), wf + 2 * (uint64_t(rank_) << L_), local_amps() * sizeof(double2),
+                                  cudaMemcpyHostToDevice, stream_));
+    else
+        PQB_CHECK(cudaMemsetAsync(psi(), 0, local_amps() * sizeof(double2), stream_));
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+}
+
+size_t Engine::cheat_map(uint32_t* ids, uint32_t* pos, size_t cap) {
+    run();
+    size_t i = 0;
+    for (auto& kv : map_) {
+        if (i < cap) {
+            ids[i] = kv.first;
+            pos[i] = kv.second;
+        }
+        ++i;
+    }
+    return i;
+}
+
+void Engine::cheat_state(double* out, size_t cap_amps) {
+    run();
+    const uint64_t total = uint64_t(1) << n_;
+    if (cap_amps < total) throw ValueErr("cheat(): output buffer too small");
+    if (!dist_) {
+        const double2* src = psi();
+        if (!layout_is_identity()) {
+            ensure_scratch(*scratch1_, local_amps() * sizeof(double2));
+            uint8_t perm[64];
+            for (int p = 0; p < n_; ++p) perm[p] = loc_[p];  // logical out bit p <- physical in bit loc_[p]
+            k::permute_gather(ctx(), psi(), scratch1_->amps(), local_amps(), n_, perm);
+            src = scratch1_->amps();
+        }
+        PQB_CHECK(cudaMemcpyAsync(out, src, total * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+        PQB_CHECK(cudaStreamSynchronize(stream_));
+        return;
+    }
+    // sharded: every rank contributes its amplitudes at their logical indices; host-side sum (small states only)
+    if (n_ > 26) throw RuntimeErr("cheat(): the sharded state is too large to gather on every rank (use get_amplitudes)");
+    std::vector<double> mine(local_amps() * 2);
+    PQB_CHECK(cudaMemcpyAsync(mine.data(), psi(), local_amps() * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+    std::memset(out, 0, total * sizeof(double2));
+    if ((uint64_t(rank_) & dist_->free_rank_bits_mask()) == 0) {
+        for (uint64_t i = 0; i < local_amps(); ++i) {
+            uint64_t logical = 0;
+            for (int p = 0; p < n_; ++p) {
+                const uint64_t bit = loc_[p] < 64 ? (i >> loc_[p]) & 1 : uint64_t((rank_ >> (loc_[p] - 64)) & 1);
+                logical |= bit << p;
+            }
+            out[2 * logical] = mine[2 * i];
+            out[2 * logical + 1] = mine[2 * i + 1];
+        }
+    }
+    dist_->allreduce_sum_vec(out, 2 * total);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// emulate_math
+// ---------------------------------------------------------------------------------------------------------------
+void Engine::emulate_math(int mode, int64_t a, int64_t N, const uint64_t* table, size_t table_len, const uint32_t* reg_ids,
+                          const uint32_t* reg_sizes, size_t n_regs, const uint32_t* ctrl, size_t nc) {
+    run();
+    if (n_regs > 16) throw ValueErr("emulate_math(): more than 16 registers");
+    if ((mode == k::MATH_ADD_MOD || mode == k::MATH_MUL_MOD) && N == 0) throw ValueErr("emulate_math(): N must not be 0");
+    k::MathDesc d{};
+    d.mode = mode;
+    d.a = a;
+    d.N = N;
+    d.n_regs = int(n_regs);
+    std::vector<uint32_t> need;
+    size_t flat = 0;
+    for (size_t r = 0; r < n_regs; ++r) {
+        d.reg_off[r] = int(flat);
+        for (uint32_t b = 0; b < reg_sizes[r]; ++b, ++flat) {
+            if (flat >= 64) throw ValueErr("emulate_math(): registers too large");
+            need.push_back(pos_of(reg_ids[flat], "emulate_math(): Unknown qubit id."));
+        }
+    }
+    d.reg_off[n_regs] = int(flat);
+    if (mode == k::MATH_TABLE && table_len != (size_t(1) << flat)) throw ValueErr("emulate_math(): table size mismatch");
+    std::vector<uint32_t> cl;
+    for (size_t i = 0; i < nc; ++i) cl.push_back(pos_of(ctrl[i], "emulate_math(): Unknown control qubit id."));
+    if (dist_) make_local(need);
+    for (size_t i = 0; i < flat; ++i) d.reg_pos[i] = loc_[need[i]];
+    bool active = true;
+    for (auto lp : cl) {
+        if (is_local(lp))
+            d.ctrl_mask |= uint64_t(1) << loc_[lp];
+        else if (!((rank_ >> (loc_[lp] - 64)) & 1))
+            active = false;
+    }
+    if (!active) return;  // this rank's control bits are not all set: identity on the whole shard
+    if (mode == k::MATH_TABLE)
+        d.d_table = static_cast<const unsigned long long*>(small_upload(table, table_len * sizeof(uint64_t)));
+    const size_t bytes = local_amps() * sizeof(double2);
+    ensure_scratch(*scratch1_, bytes);
+    PQB_CHECK(cudaMemsetAsync(scratch1_->ptr(), 0, bytes, stream_));
+    k::emulate_math(ctx(), psi(), scratch1_->amps(), local_amps(), d);
+    std::swap(state_, scratch1_);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pauli-string operators
+// ---------------------------------------------------------------------------------------------------------------
+std::vector<k::PauliTerm> Engine::build_terms(const TermsView& t, const uint32_t* ids, size_t n_ids, bool skip_identity,
+                                              double* id_re, double* id_im) {
+    std::vector<k::PauliTerm> out;
+    out.reserve(t.n_terms);
+    if (id_re) *id_re = 0.0;
+    if (id_im) *id_im = 0.0;
+    for (size_t ti = 0; ti < t.n_terms; ++ti) {
+        double cre = t.complex_coeff ? t.coeff[2 * ti] : t.coeff[ti];
+        double cim = t.complex_coeff ? t.coeff[2 * ti + 1] : 0.0;
+        const size_t b = t.offsets[ti], e = t.offsets[ti + 1];
+        if (b == e && skip_identity) {
+            if (id_re) *id_re += cre;
+            if (id_im) *id_im += cim;
+            continue;
+        }
+        // compose the one-qubit Paulis left to right (apply_term queues them in this order, simulator.hpp:545-548) into
+        // phase * X^x Z^z, in *logical* bits first
+        uint64_t x = 0, z = 0;
+        int quarter = 0;  // phase = i^quarter
+        for (size_t j = b; j < e; ++j) {
+            if (t.qubit_index[j] >= n_ids) throw ValueErr("qubit operator acts on a qubit outside the given register");
+            const uint32_t lp = pos_of(ids[t.qubit_index[j]], "Pauli operator: Unknown qubit id.");
+            const uint64_t bit = uint64_t(1) << lp;
+            switch (t.pauli[j]) {
+                case 'X': x ^= bit; break;
+                case 'Z':
+                    if (x & bit) quarter += 2;
+                    z ^= bit;
+                    break;
+                case 'Y':
+                    quarter += 1;
+                    if (x & bit) quarter += 2;
+                    x ^= bit;
+                    z ^= bit;
+                    break;
+                default: throw ValueErr("Pauli operator must be 'X', 'Y' or 'Z'");
+            }
+        }
+        switch (quarter & 3) {
+            case 1: { const double r = -cim; cim = cre; cre = r; break; }
+            case 2: cre = -cre; cim = -cim; break;
+            case 3: { const double r = cim; cim = -cre; cre = r; break; }
+            default: break;
+        }
+        out.push_back(k::PauliTerm{x, z, cre, cim});
+    }
+    return out;
+}
+
+// logical masks -> local physical masks; rank-bit Z factors are folded into the coefficient
+static void to_physical(std::vector<k::PauliTerm>& terms, const std::vector<uint8_t>& loc, int n, int rank) {
+    for (auto& t : terms) {
+        uint64_t x = 0, z = 0;
+        int flip = 0;
+        for (int p = 0; p < n; ++p) {
+            const uint64_t bit = uint64_t(1) << p;
+            if (loc[p] < 64) {
+                if (t.xmask & bit) x |= uint64_t(1) << loc[p];
+                if (t.zmask & bit) z |= uint64_t(1) << loc[p];
+            } else {
+                if (t.xmask & bit) throw RuntimeErr("internal: X on a rank bit was not remapped");
+                if ((t.zmask & bit) && ((rank >> (loc[p] - 64)) & 1)) flip ^= 1;
+            }
+        }
+        t.xmask = x;
+        t.zmask = z;
+        if (flip) {
+            t.cre = -t.cre;
+            t.cim = -t.cim;
+        }
+    }
+}
+
+double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, size_t n_ids) {
+    run();
+    auto terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);
+    if (dist_) {
+        std::vector<uint32_t> need;
+        for (auto& tm : terms)
+            for (int p = 0; p < n_; ++p)
+                if ((tm.xmask >> p) & 1) need.push_back(uint32_t(p));
+        std::sort(need.begin(), need.end());
+        need.erase(std::unique(need.begin(), need.end()), need.end());
+        make_local(need);
+    }
+    to_physical(terms, loc_, n_, rank_);
+    std::stable_sort(terms.begin(), terms.end(),
+                     [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+    double* d_acc = d_scalars_;
+    PQB_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double), stream_));
+    size_t i = 0;
+    while (i < terms.size()) {
+        size_t j = i;
+        while (j < terms.size() && terms[j].xmask == terms[i].xmask && j - i < 64) ++j;
+        k::pauli_expectation_group(ctx(), psi(), L_, terms[i].xmask, &terms[i], int(j - i), d_partials_, d_acc);
+        i = j;
+    }
+    return allreduce_sum(read_scalar(d_acc));
+}
+
+void Engine::apply_qubit_operator(const TermsView& t, const uint32_t* ids, size_t n_ids) {
+    run();
+    auto terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);
+    if (dist_) {
+        std::vector<uint32_t> need;
+        for (auto& tm : terms)
+            for (int p = 0; p < n_; ++p)
+                if ((tm.xmask >> p) & 1) need.push_back(uint32_t(p));
+        std::sort(need.begin(), need.end());
+        need.erase(std::unique(need.begin(), need.end()), need.end());
+        make_local(need);
+    }
+    to_physical(terms, loc_, n_, rank_);
+    std::stable_sort(terms.begin(), terms.end(),
+                     [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+    const size_t bytes = local_amps() * sizeof(double2);
+    ensure_scratch(*scratch1_, bytes);
+    const k::PauliTerm* d_terms =
+        static_cast<const k::PauliTerm*>(small_upload(terms.data(), std::max<size_t>(1, terms.size()) * sizeof(k::PauliTerm)));
+    k::pauli_apply(ctx(), psi(), scratch1_->amps(), local_amps(), d_terms, int(terms.size()), 1.0, 0.0, nullptr, 0, nullptr,
+                   nullptr);
+    std::swap(state_, scratch1_);
+}
+
+void Engine::emulate_time_evolution(const TermsView& t, double time, const uint32_t* ids, size_t n_ids,
+                                    const uint32_t* ctrl, size_t nc) {
+    run();
+    double tr = 0.0;
+    auto terms = build_terms(t, ids, n_ids, true, &tr, nullptr);
+    double op_nrm = 0.0;
+    // |c| of the caller's coefficients (phases i^k folded in by build_terms do not change the modulus)
+    for (auto& tm : terms) op_nrm += std::hypot(tm.cre, tm.cim);
+    const unsigned s = unsigned(std::fabs(time) * op_nrm + 1.);
+    const std::complex<double> correction = std::exp(std::complex<double>(0.0, -time * tr / double(s)));
+    std::vector<uint32_t> cl;
+    for (size_t i = 0; i < nc; ++i) cl.push_back(pos_of(ctrl[i], "emulate_time_evolution(): Unknown control qubit id."));
+    if (dist_) {
+        std::vector<uint32_t> need;
+        for (auto& tm : terms)
+            for (int p = 0; p < n_; ++p)
+                if ((tm.xmask >> p) & 1) need.push_back(uint32_t(p));
+        std::sort(need.begin(), need.end());
+        need.erase(std::unique(need.begin(), need.end()), need.end());
+        make_local(need);
+    }
+    to_physical(terms, loc_, n_, rank_);
+    std::stable_sort(terms.begin(), terms.end(),
+                     [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+    uint64_t cmask = 0;
+    bool active = true;  // accumulation is masked by the controls; H itself acts everywhere (simulator.hpp:411-425)
+    for (auto lp : cl) {
+        if (is_local(lp))
+            cmask |= uint64_t(1) << loc_[lp];
+        else if (!((rank_ >> (loc_[lp] - 64)) & 1))
+            active = false;
+    }
+    const size_t bytes = local_amps() * sizeof(double2);
+    ensure_scratch(*scratch1_, bytes);
+    ensure_scratch(*scratch2_, bytes);
+    const k::PauliTerm* d_terms =
+        static_cast<const k::PauliTerm*>(small_upload(terms.data(), std::max<size_t>(1, terms.size()) * sizeof(k::PauliTerm)));
+    double* d_norm = d_scalars_;
+    for (unsigned i = 0; i < s; ++i) {
+        double2* v = scratch1_->amps();
+        double2* u = scratch2_->amps();
+        PQB_CHECK(cudaMemcpyAsync(v, psi(), bytes, cudaMemcpyDeviceToDevice, stream_));
+        double nrm_change = 1.0;
+        for (unsigned kk = 0; nrm_change > 1.e-12; ++kk) {
+            // coeff = (-time * I) / (s * (k + 1))
+            const double cim = -time / double(s * (kk + 1));
+            if (active) {
+                k::pauli_apply(ctx(), v, u, local_amps(), d_terms, int(terms.size()), 0.0, cim, psi(), cmask, d_partials_,
+                               d_norm);
+                nrm_change = read_scalar(d_norm);
+            } else {
+                k::pauli_apply(ctx(), v, u, local_amps(), d_terms, int(terms.size()), 0.0, cim, nullptr, 0, nullptr, nullptr);
+                nrm_change = 0.0;
+            }
+            nrm_change = std::sqrt(allreduce_sum(nrm_change));
+            std::swap(v, u);
+        }
+        if (active) k::scale_masked(ctx(), psi(), local_amps(), cmask, correction.real(), correction.imag());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// additions
+// ---------------------------------------------------------------------------------------------------------------
+void Engine::apply_gate_stream(const void* packed, size_t n_bytes, size_t n_gates, bool fuse) {
+    const uint8_t* p = static_cast<const uint8_t*>(packed);
+    const uint8_t* end = p + n_bytes;
+    std::vector<double> m;
+    for (size_t g = 0; g < n_gates; ++g) {
+        if (p + 8 > end) throw ValueErr("apply_gate_stream(): truncated stream");
+        uint32_t k, nc;
+        std::memcpy(&k, p, 4);
+        std::memcpy(&nc, p + 4, 4);
+        p += 8;
+        if (k == 0 || k > 5 || nc > 64) throw ValueErr("apply_gate_stream(): bad gate header");
+        const size_t d = size_t(1) << k;
+        const size_t need = 4 * (k + nc) + 16 * d * d;
+        if (p + need > end) throw ValueErr("apply_gate_stream(): truncated stream");
+        uint32_t ids[8], ctrl[64];
+        std::memcpy(ids, p, 4 * k);
+        std::memcpy(ctrl, p + 4 * k, 4 * nc);
+        m.resize(2 * d * d);
+        std::memcpy(m.data(), p + 4 * (k + nc), 16 * d * d);
+        p += need;
+        apply_controlled_gate(m.data(), ids, k, ctrl, nc);
+        if (!fuse) run();
+    }
+}
+
+void Engine::init_random_state(uint32_t n_qubits, uint64_t seed) {
+    fuser_.clear();
+    if (n_qubits > 40) throw ValueErr("init_random_state(): too many qubits");
+    map_.clear();
+    loc_.clear();
+    n_ = int(n_qubits);
+    int g = 0;
+    if (dist_) {
+        g = std::min<int>(dist_->rank_bits(), n_);
+        dist_->reset_rank_bits(g);
+    }
+    L_ = n_ - g;
+    for (int p = 0; p < n_; ++p) {
+        map_[uint32_t(p)] = uint32_t(p);
+        loc_.push_back(uint8_t(p < L_ ? p : 64 + (p - L_)));
+    }
+    try {
+        state_->ensure(local_amps() * sizeof(double2));
+    } catch (const std::bad_alloc&) {
+        scratch1_->release();
+        scratch2_->release();
+        try {
+            state_->ensure(local_amps() * sizeof(double2));
+        } catch (const std::bad_alloc&) {
+            throw CudaErr("init_random_state(): out of device memory");
+        }
+    }
+    const bool active = !dist_ || uint64_t(rank_) < (uint64_t(1) << g);
+    if (active)
+        k::init_random(ctx(), psi(), local_amps(), seed, uint64_t(rank_) << L_);
+    else
+        PQB_CHECK(cudaMemsetAsync(psi(), 0, local_amps() * sizeof(double2), stream_));
+    const double nrm = norm_squared();
+    k::scale_all(ctx(), psi(), local_amps(), 1.0 / std::sqrt(nrm));
+}
+
+void Engine::synchronize() { PQB_CHECK(cudaStreamSynchronize(stream_)); }
+
+void Engine::timer_start() { PQB_CHECK(cudaEventRecord(ev0_, stream_)); }
+
+double Engine::timer_stop() {
+    PQB_CHECK(cudaEventRecord(ev1_, stream_));
+    PQB_CHECK(cudaEventSynchronize(ev1_));
+    float ms = 0.f;
+    PQB_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return double(ms);
+}
+
+void Engine::flush_l2(size_t bytes) {
+    if (bytes > d_flush_cap_) {
+        PQB_CHECK(cudaStreamSynchronize(stream_));
+        if (d_flush_) cudaFree(d_flush_);
+        PQB_CHECK(cudaMalloc(&d_flush_, bytes));
+        d_flush_cap_ = bytes;
+    }
+    k::flush_l2(ctx(), d_flush_, bytes / sizeof(double));
+}
+
+double Engine::bench_dense_pass(const double* m, const uint32_t* positions, size_t kq, uint64_t ctrl_mask, int repeats) {
+    run();
+    if (kq == 0 || kq > 5) throw ValueErr("bench_dense_pass(): k must be 1..5");
+    uint8_t tpos[8], cpos[64];
+    int nc = 0;
+    for (size_t i = 0; i < kq; ++i) {
+        if (int(positions[i]) >= L_) throw ValueErr("bench_dense_pass(): position outside the local state");
+        tpos[i] = uint8_t(positions[i]);
+    }
+    std::sort(tpos, tpos + kq);
+    for (int b = 0; b < L_; ++b)
+        if ((ctrl_mask >> b) & 1) cpos[nc++] = uint8_t(b);
+    if (repeats < 1) repeats = 1;
+    k::apply_dense(ctx(), psi(), L_, int(kq), tpos, nc, cpos, m);  // warm-up
+    timer_start();
+    for (int r = 0; r < repeats; ++r) k::apply_dense(ctx(), psi(), L_, int(kq), tpos, nc, cpos, m);
+    return timer_stop() / repeats;
+}
+
+double Engine::measure_fp64_peak() { return k::measure_fp64_tflops(ctx(), sm_count_); }
+
+double Engine::measure_copy_bandwidth(size_t bytes) {
+    ensure_scratch(*scratch1_, bytes);
+    ensure_scratch(*scratch2_, bytes);
+    PQB_CHECK(cudaMemsetAsync(scratch1_->ptr(), 1, bytes, stream_));
+    double best = 0.0;
+    for (int r = 0; r < 6; ++r) {
+        timer_start();
+        PQB_CHECK(cudaMemcpyAsync(scratch2_->ptr(), scratch1_->ptr(), bytes, cudaMemcpyDeviceToDevice, stream_));
+        const double ms = timer_stop();
+        const double gbs = 2.0 * double(bytes) / (ms * 1e-3) / 1e9;
+        if (r > 0 && gbs > best) best = gbs;
+    }
+    return best;
+}
+
+}  // namespace pqb

@@ -1,0 +1,146 @@
+// Host controller of the B200 state-vector engine: qubit bookkeeping, RNG replay, fuser, kernel orchestration.
+//
+// Replaces `class Simulator` (reference: projectq/backends/_sim/_cppkernels/simulator.hpp:37-578).  The logical
+// bookkeeping (id -> bit position, new qubit = new most-significant bit, positions shift down on deallocation) is the
+// reference's, bit for bit, because cheat() exposes it.  Underneath, every logical position is placed on a physical bit:
+// either a bit of the local amplitude index or, in a sharded run, a bit of the rank number.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/pqb200.h"
+#include "devmem.h"
+#include "fuser.h"
+#include "kernels.cuh"
+
+namespace pqb {
+
+// error classes mirrored onto pqb_status by capi.cpp
+struct RuntimeErr : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct ValueErr : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct CudaErr : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+class Dist;  // sharded-state communicator (dist.h)
+
+struct TermsView {
+    size_t n_terms;
+    const size_t* offsets;
+    const uint32_t* qubit_index;
+    const char* pauli;
+    const double* coeff;  // real: n_terms, complex: 2*n_terms
+    bool complex_coeff;
+};
+
+class Engine {
+public:
+    Engine(uint32_t seed, const pqb_opts& opts);
+    ~Engine();
+
+    void allocate_qubit(uint32_t id);
+    void deallocate_qubit(uint32_t id);
+    bool get_classical_value(uint32_t id, double tol);
+    bool is_classical(uint32_t id, double tol);
+    void measure_qubits(const uint32_t* ids, size_t n, uint8_t* out);
+    void apply_controlled_gate(const double* m, const uint32_t* ids, size_t k, const uint32_t* ctrl, size_t nc);
+    void emulate_math(int mode, int64_t a, int64_t N, const uint64_t* table, size_t table_len, const uint32_t* reg_ids,
+                      const uint32_t* reg_sizes, size_t n_regs, const uint32_t* ctrl, size_t nc);
+    double get_expectation_value(const TermsView& t, const uint32_t* ids, size_t n_ids);
+    void apply_qubit_operator(const TermsView& t, const uint32_t* ids, size_t n_ids);
+    void emulate_time_evolution(const TermsView& t, double time, const uint32_t* ids, size_t n_ids, const uint32_t* ctrl,
+                                size_t nc);
+    double get_probability(const uint8_t* bits, const uint32_t* ids, size_t n);
+    std::complex<double> get_amplitude(const uint8_t* bits, const uint32_t* ids, size_t n);
+    void set_wavefunction(const double* wf, size_t n_amps, const uint32_t* ordering, size_t n);
+    void collapse_wavefunction(const uint32_t* ids, size_t n_ids, const uint8_t* values, size_t n_values);
+    void run();
+    size_t num_qubits() const { return size_t(n_); }
+    size_t cheat_map(uint32_t* ids, uint32_t* pos, size_t cap);
+    void cheat_state(double* out, size_t cap_amps);
+
+    // additions
+    void get_amplitudes(const uint64_t* logical_idx, size_t n, double* out);
+    void apply_gate_stream(const void* packed, size_t n_bytes, size_t n_gates, bool fuse);
+    void init_random_state(uint32_t n_qubits, uint64_t seed);
+    double norm_squared();
+    void synchronize();
+    void timer_start();
+    double timer_stop();
+    void get_stats(pqb_stats* out) const { *out = stats_; }
+    void reset_stats() { stats_ = pqb_stats{}; }
+    void flush_l2(size_t bytes);
+    double bench_dense_pass(const double* m, const uint32_t* positions, size_t k, uint64_t ctrl_mask, int repeats);
+    double measure_fp64_peak();
+    double measure_copy_bandwidth(size_t bytes);
+
+    std::string last_error;
+
+private:
+    k::Ctx ctx() { return k::Ctx{stream_, &stats_.kernel_launches}; }
+    uint64_t local_amps() const { return uint64_t(1) << L_; }
+    double2* psi() { return state_->amps(); }
+    uint32_t pos_of(uint32_t id, const char* what) const;
+    bool known(uint32_t id) const { return map_.count(id) != 0; }
+    // physical placement
+    bool is_local(uint32_t logical_pos) const { return loc_[logical_pos] < 64; }
+    uint64_t logical_to_local_index(uint64_t logical_index, bool* mine) const;
+    bool layout_is_identity() const;
+    // split a logical (mask, val) into the local part; returns false if this rank's bits contradict val
+    bool split_mask(uint64_t lmask, uint64_t lval, uint64_t* local_mask, uint64_t* local_val) const;
+    double read_scalar(const double* d_ptr);
+    double allreduce_sum(double v);
+    void ensure_scratch(GrowBuffer& b, size_t bytes);
+    void swap_state(GrowBuffer*& other);
+    std::vector<k::PauliTerm> build_terms(const TermsView& t, const uint32_t* ids, size_t n_ids, bool skip_identity,
+                                          double* identity_sum_re, double* identity_sum_im);
+    void make_local(const std::vector<uint32_t>& logical_positions);
+    void apply_pass(const FusedPass& p);
+    unsigned long long last_probe_[2] = {~0ULL, ~0ULL};  // result of the last classical probe (bit 0, bit 1)
+    double draw_uniform();
+
+    // device
+    int device_ = 0;
+    int sm_count_ = 148;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    GrowBuffer buf_[3];
+    GrowBuffer* state_ = &buf_[0];
+    GrowBuffer* scratch1_ = &buf_[1];
+    GrowBuffer* scratch2_ = &buf_[2];
+    double* d_partials_ = nullptr;         // kReducePartials doubles
+    double* d_scalars_ = nullptr;          // small device scratch (bins, accumulators)
+    double* h_pinned_ = nullptr;           // pinned host mirror of d_scalars_
+    void* d_small_ = nullptr;              // terms / indices / tables upload area
+    size_t d_small_cap_ = 0;
+    double* d_flush_ = nullptr;
+    size_t d_flush_cap_ = 0;
+    void* small_upload(const void* src, size_t bytes);
+
+    // logical bookkeeping (reference: map_, N_)
+    std::map<uint32_t, uint32_t> map_;  // qubit id -> logical bit position
+    int n_ = 0;
+    // physical placement
+    int L_ = 0;                  // local index bits
+    std::vector<uint8_t> loc_;   // logical position -> local bit (< 64) or 64 + rank bit
+
+    std::mt19937 rng_;
+    Fuser fuser_;
+    int fusion_max_ = 5;
+    pqb_stats stats_{};
+    std::unique_ptr<Dist> dist_;
+    int rank_ = 0, world_ = 1;
+};
+
+}  // namespace pqb

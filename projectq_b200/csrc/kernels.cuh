@@ -1,0 +1,91 @@
+// Launchers of the sm_100a kernels (kernels.cu).  Host code only sees these plain functions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace pqb {
+namespace k {
+
+// launch context: the engine's stream and its launch counter (pqb_stats.kernel_launches)
+struct Ctx {
+    cudaStream_t stream;
+    uint64_t* launches;
+};
+
+constexpr int kMaxDense = 5;        // widest dense gate (reference: simulator.hpp:522-523 throws above 5)
+constexpr int kReducePartials = 65536;  // capacity (in doubles) of the partial-sum scratch the reductions use
+
+// One fused dense pass (reference: kernel<k>, intrin/kernel1..5.hpp).  n_bits = log2(#local amplitudes).
+// tpos: ascending bit positions of the k targets (matrix bit l <-> tpos[l]); cpos: ascending control positions.
+// m_host: 2^k x 2^k row-major (re,im).
+void apply_dense(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
+                 const double* m_host);
+// Diagonal pass: psi[i] *= d[bits of i at tpos] on the control-satisfying subspace; d_host has 2^k (re,im) entries.
+void apply_diagonal(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl,
+                    const uint8_t* cpos, const double* d_host);
+
+// sum_{(i & mask) == val} |psi_i|^2 -> d_out[0]  (reference: get_probability, simulator.hpp:363-367)
+void norm_masked(const Ctx& c, const double2* psi, uint64_t n_amps, uint64_t mask, uint64_t val, double* d_partials,
+                 double* d_out);
+// psi_i <- (i & mask) == val ? psi_i * scale : 0   (reference: simulator.hpp:174-185, 478-484)
+void collapse_scale(const Ctx& c, double2* psi, uint64_t n_amps, uint64_t mask, uint64_t val, double scale);
+// psi_i *= scale
+void scale_all(const Ctx& c, double2* psi, uint64_t n_amps, double scale);
+// d_out2[b] = min over amplitudes with |psi|^2 > tol and bit `pos` == b of the *logical* index with that bit removed
+// (UINT64_MAX if none): decides is_classical / get_classical_value (reference: simulator.hpp:76-108).
+// phys2log: logical bit of each physical bit, or nullptr for the identity layout.  rank_bits: this rank's physical
+// high bits (already shifted), 0 on a single GPU.
+void classical_probe(const Ctx& c, const double2* psi, uint64_t n_amps, int pos_phys, int pos_log, double tol,
+                     const uint8_t* phys2log, int n_total_bits, uint64_t rank_bits, unsigned long long* d_out2);
+// out[j] = in[insert bit `pos` = value into j]  (reference: collapse_vector shrink branch, simulator.hpp:123-133)
+void compact_bit(const Ctx& c, const double2* in, double2* out, uint64_t n_out, int pos, int value);
+// out[i] = in[permute(i)], in-index bit perm[b] <- out-index bit b
+void permute_gather(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, int n_bits, const uint8_t* perm);
+// out[j] = psi[indices[j]] for a handful of indices
+void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices, uint64_t n, double2* d_out);
+
+// Measurement search support (reference: the serial inverse-CDF scan, simulator.hpp:156-158): sums of |psi|^2 over
+// bins.  The subspace is fixed_val on the positions in ins_pos that are neither bin bits; bin b covers the amplitudes
+// whose bits at bin_pos spell b.  ins_pos = ascending union of the fixed positions and bin positions.
+// d_bins receives 2^m doubles (each bin reduced in a fixed order -> run-to-run deterministic).
+void bin_sums(const Ctx& c, const double2* psi, int n_bits, int n_ins, const uint8_t* ins_pos, uint64_t fixed_val, int m,
+              const uint8_t* bin_pos, double* d_partials, double* d_bins);
+
+// emulate_math (reference: simulator.hpp:224-290): out[pi(i)] += in[i]; `out` must be zeroed by the caller.
+enum MathMode { MATH_ADD = 0, MATH_ADD_MOD = 1, MATH_MUL_MOD = 2, MATH_TABLE = 3 };
+struct MathDesc {
+    int mode;
+    long long a, N;
+    const unsigned long long* d_table;  // MATH_TABLE only
+    int n_regs;
+    int reg_off[17];      // register r uses reg_pos[reg_off[r] .. reg_off[r+1])
+    uint8_t reg_pos[64];  // physical bit position of each register bit, least-significant first
+    uint64_t ctrl_mask;
+};
+void emulate_math(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const MathDesc& d);
+
+// Pauli strings in physical-bit form: (P psi)[j] = phase * (-1)^{popcount(s & zmask)} psi[s], s = j ^ xmask, with
+// phase = coefficient * i^{nY} (reference: apply_term, simulator.hpp:538-550).
+struct PauliTerm {
+    uint64_t xmask, zmask;
+    double cre, cim;
+};
+// sum_t Re<psi| c_t P_t |psi> for terms sharing one xmask (n_terms <= 64 per call); adds the result to d_acc[0].
+void pauli_expectation_group(const Ctx& c, const double2* psi, int n_bits, uint64_t xmask, const PauliTerm* terms,
+                             int n_terms, double* d_partials, double* d_acc);
+// out[j] = scale * sum_t c_t (P_t in)[j]; optionally acc[j] += out[j] where (j & ctrl_mask) == ctrl_mask and
+// d_norm[0] = sum over those j of |out[j]|^2 (one Taylor order of emulate_time_evolution, simulator.hpp:408-428).
+// d_terms must be sorted by xmask.  rank_bits/sign handling of global bits is the caller's business.
+void pauli_apply(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const PauliTerm* d_terms, int n_terms,
+                 double scale_re, double scale_im, double2* acc, uint64_t ctrl_mask, double* d_partials, double* d_norm);
+// psi_i *= (re,im) where (i & ctrl_mask) == ctrl_mask
+void scale_masked(const Ctx& c, double2* psi, uint64_t n_amps, uint64_t ctrl_mask, double re, double im);
+
+// benchmark helpers
+void init_random(const Ctx& c, double2* psi, uint64_t n_amps, uint64_t seed, uint64_t index_offset);
+void flush_l2(const Ctx& c, double* buf, uint64_t n_doubles);
+double measure_fp64_tflops(const Ctx& c, int sm_count);
+
+}  // namespace k
+}  // namespace pqb

@@ -1,0 +1,167 @@
+"""CPU tests of the host-side pieces of the path: fuser, RNG replay, remap planner, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.statevec_oracle import MT19937, OracleSimulator
+from tests.helpers import brickwork_circuit, pack_gate_stream, rand_state, rand_unitary
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    path = os.path.join(ROOT, "projectq_b200", "libpqb200.so")
+    if not os.path.exists(path):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    return ctypes.CDLL(path)
+
+
+def test_c_abi_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "pqb200.h")).read()
+    names = re.findall(r"PQB_API\s+[\w\s\*]+?\b(pqb_\w+)\s*\(", header)
+    assert len(names) >= 40
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sim = ctypes.c_void_p()
+    st = lib.pqb_create(ctypes.c_uint32(1), None, ctypes.byref(sim))
+    assert st == 3  # PQB_ERR_CUDA
+    lib.pqb_last_error.restype = ctypes.c_char_p
+    assert b"no CUDA device" in lib.pqb_last_error(None)
+
+
+def test_rng_stream_matches_libstdcxx_golden(lib):
+    out = (ctypes.c_double * 6)()
+    assert lib.pqb_host_rng_stream(ctypes.c_uint32(1), ctypes.c_size_t(6), out) == 0
+    want = [0.99718480823026556, 0.93255736136816547, 0.128124447772306, 0.99904051546527362]
+    assert list(out)[:4] == want
+    r = MT19937(1)
+    assert list(out) == [r.uniform01() for _ in range(6)]
+    for seed in (0, 7, 4294967295):
+        assert lib.pqb_host_rng_stream(ctypes.c_uint32(seed), ctypes.c_size_t(6), out) == 0
+        r = MT19937(seed)
+        assert list(out) == [r.uniform01() for _ in range(6)]
+
+
+def fuse(lib, gates, max_qubits):
+    body, n = pack_gate_stream(gates)
+    cap = len(body) * 8 + (1 << 20)
+    out = ctypes.create_string_buffer(cap)
+    used = ctypes.c_size_t()
+    passes = ctypes.c_size_t()
+    st = lib.pqb_host_fuse_stream(body, ctypes.c_size_t(len(body)), ctypes.c_size_t(n), ctypes.c_int(max_qubits), out,
+                                  ctypes.c_size_t(cap), ctypes.byref(used), ctypes.byref(passes))
+    assert st == 0
+    raw = out.raw[: used.value]
+    res = []
+    off = 0
+    for _ in range(passes.value):
+        k, nc = np.frombuffer(raw, dtype=np.uint32, count=2, offset=off)
+        off += 8
+        ids = np.frombuffer(raw, dtype=np.uint32, count=int(k + nc), offset=off)
+        off += 4 * int(k + nc)
+        d = 1 << int(k)
+        m = np.frombuffer(raw, dtype=np.complex128, count=d * d, offset=off).reshape(d, d)
+        off += 16 * d * d
+        res.append((m, [int(x) for x in ids[:k]], [int(x) for x in ids[k:]]))
+    assert off == used.value
+    return res
+
+
+def run_oracle(n, wf, gates):
+    s = OracleSimulator(1)
+    for q in range(n):
+        s.allocate_qubit(q)
+    s.set_wavefunction(wf, list(range(n)))
+    for m, t, c in gates:
+        s.apply_controlled_gate(m, t, c)
+    return s.cheat()[1]
+
+
+@pytest.mark.parametrize("max_qubits", [1, 2, 3, 4, 5])
+def test_fuser_is_amplitude_equivalent_random(lib, max_qubits):
+    rng = np.random.default_rng(40 + max_qubits)
+    n = 9
+    for trial in range(6):
+        gates = []
+        for g in range(50):
+            k = int(rng.integers(1, max_qubits + 1))
+            nc = int(rng.integers(0, 3))
+            qs = [int(x) for x in rng.permutation(n)[: k + nc]]
+            if rng.random() < 0.3:
+                m = np.diag(np.exp(1j * rng.uniform(0, 6.28, 1 << k)))
+            else:
+                m = rand_unitary(rng, k)
+            gates.append((m, qs[:k], qs[k:]))
+        passes = fuse(lib, gates, max_qubits)
+        assert all(len(t) <= max_qubits for _, t, _ in passes)
+        wf = rand_state(rng, n)
+        a = run_oracle(n, wf, gates)
+        b = run_oracle(n, wf, passes)
+        assert np.max(np.abs(a - b)) < 1e-12
+
+
+def test_fuser_packs_brickwork_densely(lib):
+    n, depth = 16, 20
+    gates = brickwork_circuit(n, depth)
+    passes = fuse(lib, gates, 5)
+    assert len(passes) * 6 < len(gates)  # at least 6 gates per pass on average
+    wf = rand_state(np.random.default_rng(1), n)
+    assert np.max(np.abs(run_oracle(n, wf, gates) - run_oracle(n, wf, passes))) < 1e-12
+    # width 1 = no fusion: one pass per gate, controls stay controls (CNOT = k=1 + control mask)
+    p1 = fuse(lib, gates, 1)
+    assert len(gates) - 2 * depth <= len(p1) <= len(gates)  # only back-to-back gates on one idle qubit merge
+    assert sum(len(c) for _, _, c in p1) == sum(len(c) for _, _, c in gates)
+    assert all(len(t) == 1 for _, t, _ in p1)
+
+
+def test_fuser_keeps_common_controls_global(lib):
+    rng = np.random.default_rng(9)
+    gates = [(rand_unitary(rng, 1), [q], [7, 8]) for q in range(4)]
+    passes = fuse(lib, gates, 5)
+    assert len(passes) == 1
+    m, t, c = passes[0]
+    assert sorted(c) == [7, 8] and sorted(t) == [0, 1, 2, 3]
+    # a gate lacking control 8 demotes it into the matrix
+    gates.append((rand_unitary(rng, 1), [0], [7]))
+    passes = fuse(lib, gates, 5)
+    assert len(passes) == 1 and passes[0][2] == [7] and sorted(passes[0][1]) == [0, 1, 2, 3, 8]
+    n = 9
+    wf = rand_state(rng, n)
+    assert np.max(np.abs(run_oracle(n, wf, gates) - run_oracle(n, wf, passes))) < 1e-12
+
+
+def test_remap_planner(lib):
+    # 2 rank bits, 6 local bits: logical 0,1 on rank bits 0,1; logical 2..7 on local bits 0..5
+    loc = (ctypes.c_uint8 * 8)(64, 65, 0, 1, 2, 3, 4, 5)
+    need = (ctypes.c_uint32 * 3)(0, 7, 3)
+    pairs = (ctypes.c_int32 * 8)()
+    n_pairs = ctypes.c_size_t()
+    st = lib.pqb_host_plan_remap(loc, ctypes.c_size_t(8), ctypes.c_int(6), need, ctypes.c_size_t(3), pairs,
+                                 ctypes.c_size_t(4), ctypes.byref(n_pairs))
+    assert st == 0 and n_pairs.value == 1
+    # logical 7 sits on the top local bit (5) and is needed, so the victim is local bit 4 (logical 6)
+    assert (pairs[0], pairs[1]) == (0, 4)
+    assert list(loc) == [4, 65, 0, 1, 2, 3, 64, 5]
+    # everything local already -> no swaps
+    st = lib.pqb_host_plan_remap(loc, ctypes.c_size_t(8), ctypes.c_int(6), need, ctypes.c_size_t(3), pairs,
+                                 ctypes.c_size_t(4), ctypes.byref(n_pairs))
+    assert st == 0 and n_pairs.value == 0
+    # impossible: more needed qubits than local bits
+    loc2 = (ctypes.c_uint8 * 3)(64, 0, 1)
+    need2 = (ctypes.c_uint32 * 3)(0, 1, 2)
+    st = lib.pqb_host_plan_remap(loc2, ctypes.c_size_t(3), ctypes.c_int(2), need2, ctypes.c_size_t(3), pairs,
+                                 ctypes.c_size_t(4), ctypes.byref(n_pairs))
+    assert st == 1
