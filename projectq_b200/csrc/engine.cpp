@@ -631,10 +631,11 @@ void Engine::get_amplitudes(const uint64_t* logical_idx, size_t n, double* out) 
         local[i] = logical_to_local_index(logical_idx[i], &ok);
         mine[i] = ok;
     }
-    std::vector<uint64_t> staged(3 * n, 0);  // n indices followed by room for n amplitudes
-    std::copy(local.begin(), local.end(), staged.begin());
-    uint64_t* d_idx = static_cast<uint64_t*>(small_upload(staged.data(), staged.size() * sizeof(uint64_t)));
-    double2* d_out = reinterpret_cast<double2*>(d_idx + n);
+    // device staging: room for n amplitudes (16-byte aligned) followed by the n indices
+    std::vector<uint64_t> staged(3 * n, 0);
+    std::copy(local.begin(), local.end(), staged.begin() + 2 * n);
+    double2* d_out = static_cast<double2*>(small_upload(staged.data(), staged.size() * sizeof(uint64_t)));
+    const uint64_t* d_idx = reinterpret_cast<const uint64_t*>(d_out + n);
     k::gather_indices(ctx(), psi(), d_idx, n, d_out);
     PQB_CHECK(cudaMemcpyAsync(out, d_out, n * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
     PQB_CHECK(cudaStreamSynchronize(stream_));
@@ -890,7 +891,8 @@ void Engine::apply_qubit_operator(const TermsView& t, const uint32_t* ids, size_
     const size_t bytes = local_amps() * sizeof(double2);
     ensure_scratch(*scratch1_, bytes);
     const k::PauliTerm* d_terms =
-        static_cast<const k::PauliTerm*>(small_upload(terms.data(), std::max<size_t>(1, terms.size()) * sizeof(k::PauliTerm)));
+        terms.empty() ? nullptr
+                      : static_cast<const k::PauliTerm*>(small_upload(terms.data(), terms.size() * sizeof(k::PauliTerm)));
     k::pauli_apply(ctx(), psi(), scratch1_->amps(), local_amps(), d_terms, int(terms.size()), 1.0, 0.0, nullptr, 0, nullptr,
                    nullptr);
     std::swap(state_, scratch1_);
@@ -932,7 +934,8 @@ void Engine::emulate_time_evolution(const TermsView& t, double time, const uint3
     ensure_scratch(*scratch1_, bytes);
     ensure_scratch(*scratch2_, bytes);
     const k::PauliTerm* d_terms =
-        static_cast<const k::PauliTerm*>(small_upload(terms.data(), std::max<size_t>(1, terms.size()) * sizeof(k::PauliTerm)));
+        terms.empty() ? nullptr
+                      : static_cast<const k::PauliTerm*>(small_upload(terms.data(), terms.size() * sizeof(k::PauliTerm)));
     double* d_norm = d_scalars_;
     for (unsigned i = 0; i < s; ++i) {
         double2* v = scratch1_->amps();
