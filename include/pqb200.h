@@ -44,7 +44,7 @@ enum pqb_status {
 /* Options beyond the reference constructor (simulator.hpp:48 takes only the seed).  Zero-initialise for defaults. */
 typedef struct pqb_opts {
     int32_t device;            /* CUDA device ordinal (default 0) */
-    int32_t fusion_max_qubits; /* widest fused dense gate, 1..5 (0 -> 5; reference window is 4..5, simulator.hpp:48-49) */
+    int32_t fusion_max_qubits; /* widest fused dense gate, 1..5; 0 -> pick 4 or 5 per flush by cost (reference window: 4..5, simulator.hpp:48-49) */
     int32_t rank;              /* this process' rank in the sharded state (default 0) */
     int32_t world_size;        /* number of ranks = GPUs holding shards; power of two (0/1 -> single GPU) */
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (required when world_size > 1) */

@@ -30,7 +30,7 @@ constexpr int kBinBits = 10;             // measurement search: logical bits res
 // ---------------------------------------------------------------------------------------------------------------
 Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
     device_ = o.device;
-    fusion_max_ = o.fusion_max_qubits <= 0 ? 5 : std::min(o.fusion_max_qubits, 5);
+    fusion_max_ = o.fusion_max_qubits <= 0 ? 0 : std::min(o.fusion_max_qubits, 5);  // 0 = choose per flush
     rank_ = o.rank;
     world_ = o.world_size <= 1 ? 1 : o.world_size;
     if (world_ & (world_ - 1)) throw ValueErr("pqb_create: world_size must be a power of two");
@@ -404,9 +404,30 @@ void Engine::run() {
         if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
         return loc_[it->second];
     };
+    // Relative cost of one pass by width, measured on B200 (profiles/): k <= 4 runs at the HBM roofline (32 B/amplitude),
+    // k = 5 is bound by the FP64 pipe (256 flop/amplitude) and takes ~2.4x as long, so a 5-wide pass only pays off when
+    // it swallows that many more gates.  A control bit halves the amplitudes a pass touches.
+    auto cost = [](const std::vector<FusedPass>& ps) {
+        double c = 0.0;
+        for (auto& p : ps) {
+            double w = (!p.diagonal && p.targets.size() >= 5) ? 2.4 : 1.0;
+            for (size_t i = 0; i < p.ctrls.size() && i < 6; ++i) w *= 0.5;
+            c += w + 0.002;  // + launch overhead so tiny states prefer fewer passes
+        }
+        return c;
+    };
     std::vector<FusedPass> passes;
     try {
-        passes = fuser_.drain(fusion_max_, key);
+        if (fusion_max_ > 0) {
+            passes = fuser_.drain(fusion_max_, key);
+        } else {
+            passes = fuser_.plan(4, key);
+            if (passes.size() > 1) {
+                auto wide = fuser_.plan(5, key);
+                if (cost(wide) < cost(passes)) passes.swap(wide);
+            }
+            fuser_.clear();
+        }
     } catch (...) {
         fuser_.clear();  // never leave a poisoned queue behind (the reference does, simulator.hpp:522-526)
         throw;

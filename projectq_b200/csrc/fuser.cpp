@@ -160,6 +160,12 @@ void Fuser::reorder(FusedPass& p, const std::function<uint64_t(uint32_t)>& sort_
 }
 
 std::vector<FusedPass> Fuser::drain(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key) {
+    std::vector<FusedPass> passes = plan(max_qubits, sort_key);
+    pending_.clear();
+    return passes;
+}
+
+std::vector<FusedPass> Fuser::plan(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key) const {
     std::vector<FusedPass> passes;
     const size_t m = pending_.size();
     if (m == 0) return passes;
@@ -230,7 +236,6 @@ std::vector<FusedPass> Fuser::drain(int max_qubits, const std::function<uint64_t
         }
         passes.push_back(fuse(members, sort_key));
     }
-    pending_.clear();
     return passes;
 }
 

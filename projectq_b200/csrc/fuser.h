@@ -40,6 +40,8 @@ public:
     // Schedule every pending gate into passes of at most max_qubits targets (gates wider than that keep their own
     // width).  sort_key(id) orders the target qubits of a pass (the engine passes the bit position).
     std::vector<FusedPass> drain(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key);
+    // Same schedule, but the pending gates stay queued (used to compare fusion widths before committing to one).
+    std::vector<FusedPass> plan(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key) const;
 
     // Fuse an explicit list of gates (already chosen to fit) into one pass.
     static FusedPass fuse(const std::vector<const Gate*>& gates, const std::function<uint64_t(uint32_t)>& sort_key);

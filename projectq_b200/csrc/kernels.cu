@@ -85,71 +85,103 @@ static int reduce_grid(uint64_t work_items, int per_block) {
 template <int K>
 struct DenseArgs {
     double2 m[(1 << K) * (1 << K)];
-    uint64_t n_groups;
+    uint64_t n_items;  // amplitude groups to process
     uint64_t ctrl_mask;
     int n_ins;
     uint8_t tpos[8];
     uint8_t ins_pos[64];
 };
 
-template <int K, int U, int THREADS>
-__global__ void __launch_bounds__(THREADS) apply_dense_kernel(double2* __restrict__ psi,
+// 256-bit global accesses (sm_100 LDG.E.256 / STG.E.256): two adjacent amplitudes per lane, so every lane moves a full
+// 32-byte sector even when bit 0 is a target or the groups of neighbouring lanes interleave.
+__device__ __forceinline__ void ld256(const double2* ptr, double2& a, double2& b) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(ptr));
+}
+__device__ __forceinline__ void st256(double2* ptr, const double2& a, const double2& b) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
+template <int K>
+__device__ __forceinline__ void matvec_row(const DenseArgs<K>& p, const double2* v, int i, double& re, double& im) {
+    constexpr int D = 1 << K;
+    re = 0.0;
+    im = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const double2 mij = p.m[i * D + j];
+        re = fma(mij.x, v[j].x, re);
+        re = fma(-mij.y, v[j].y, re);
+        im = fma(mij.x, v[j].y, im);
+        im = fma(mij.y, v[j].x, im);
+    }
+}
+
+// MODE 0: U groups per thread, 128-bit accesses.  With bit 0 free, neighbouring lanes own neighbouring amplitudes, so
+//         every 32-byte sector a warp touches is fully used whatever the targets are.
+// MODE 1: bit 0 is a target: neighbouring lanes are >= 2 amplitudes apart and a 128-bit access would use half of each
+//         sector per instruction (measured: 3.9 TB/s instead of 6.9 TB/s); members (2j, 2j+1) of a group are adjacent,
+//         so they move as one 256-bit access instead.
+template <int K, int MODE, int U, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) apply_dense_kernel(double2* __restrict__ psi,
                                                               const __grid_constant__ DenseArgs<K> p) {
     constexpr int D = 1 << K;
     uint64_t stride[K];
 #pragma unroll
     for (int l = 0; l < K; ++l) stride[l] = uint64_t(1) << p.tpos[l];
-
+    auto offset = [&](int j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int l = 0; l < K; ++l)
+            if ((j >> l) & 1) off += stride[l];
+        return off;
+    };
     const uint64_t g0 = (uint64_t(blockIdx.x) * THREADS + threadIdx.x);
     const uint64_t gstep = uint64_t(gridDim.x) * THREADS;
 
-    double2 v[U][D];
-    uint64_t base[U];
+    if constexpr (MODE == 0) {
+        double2 v[U][D];
+        uint64_t base[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint64_t g = g0 + u * gstep;
-        if (g < p.n_groups) {
-            base[u] = insert_zero_bits(g, p.ins_pos, p.n_ins) | p.ctrl_mask;
+        for (int u = 0; u < U; ++u) {
+            const uint64_t g = g0 + u * gstep;
+            if (g < p.n_items) {
+                base[u] = insert_zero_bits(g, p.ins_pos, p.n_ins) | p.ctrl_mask;
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                uint64_t off = 0;
-#pragma unroll
-                for (int l = 0; l < K; ++l)
-                    if ((j >> l) & 1) off += stride[l];
-                v[u][j] = psi[base[u] + off];
+                for (int j = 0; j < D; ++j) v[u][j] = psi[base[u] + offset(j)];
             }
         }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint64_t g = g0 + u * gstep;
-        if (g < p.n_groups) {
+        for (int u = 0; u < U; ++u) {
+            const uint64_t g = g0 + u * gstep;
+            if (g < p.n_items) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                double re = 0.0, im = 0.0;
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const double2 mij = p.m[i * D + j];
-                    re = fma(mij.x, v[u][j].x, re);
-                    re = fma(-mij.y, v[u][j].y, re);
-                    im = fma(mij.x, v[u][j].y, im);
-                    im = fma(mij.y, v[u][j].x, im);
+                for (int i = 0; i < D; ++i) {
+                    double re, im;
+                    matvec_row<K>(p, v[u], i, re, im);
+                    psi[base[u] + offset(i)] = make_double2(re, im);
                 }
-                uint64_t off = 0;
-#pragma unroll
-                for (int l = 0; l < K; ++l)
-                    if ((i >> l) & 1) off += stride[l];
-                psi[base[u] + off] = make_double2(re, im);
             }
+        }
+    } else if constexpr (MODE == 1) {
+        if (g0 >= p.n_items) return;
+        const uint64_t base = insert_zero_bits(g0, p.ins_pos, p.n_ins) | p.ctrl_mask;
+        double2 v[D];
+#pragma unroll
+        for (int j = 0; j < D; j += 2) ld256(psi + base + offset(j), v[j], v[j + 1]);
+#pragma unroll
+        for (int i = 0; i < D; i += 2) {
+            double re0, im0, re1, im1;
+            matvec_row<K>(p, v, i, re0, im0);
+            matvec_row<K>(p, v, i + 1, re1, im1);
+            st256(psi + base + offset(i), make_double2(re0, im0), make_double2(re1, im1));
         }
     }
 }
 
-template <int K, int U, int THREADS>
-static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
-                         const double* m_host) {
+template <int K>
+static void fill_dense_args(DenseArgs<K>& args, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
+                            const double* m_host) {
     constexpr int D = 1 << K;
-    static DenseArgs<K> args;  // staging for the parameter block (copied by the launch)
     for (int i = 0; i < D * D; ++i) args.m[i] = make_double2(m_host[2 * i], m_host[2 * i + 1]);
     // ascending merge of target and control positions
     int a = 0, b = 0, n = 0;
@@ -166,12 +198,31 @@ static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* 
     args.ctrl_mask = cmask;
     for (int l = 0; l < K; ++l) args.tpos[l] = tpos[l];
     if (n > n_bits) throw std::invalid_argument("apply_dense: more target/control bits than state bits");
-    args.n_groups = uint64_t(1) << (n_bits - n);
+    args.n_items = uint64_t(1) << (n_bits - n);
+}
+
+template <int K, int MODE, int U, int THREADS, int MINB>
+static void launch_dense_mode(const Ctx& c, double2* psi, const DenseArgs<K>& args) {
     const uint64_t per_block = uint64_t(THREADS) * U;
-    const uint64_t blocks = (args.n_groups + per_block - 1) / per_block;
+    const uint64_t blocks = (args.n_items + per_block - 1) / per_block;
     if (blocks > 0x7fffffffULL) throw std::invalid_argument("apply_dense: grid too large");
-    apply_dense_kernel<K, U, THREADS><<<unsigned(blocks), THREADS, 0, c.stream>>>(psi, args);
+    apply_dense_kernel<K, MODE, U, THREADS, MINB><<<unsigned(blocks), THREADS, 0, c.stream>>>(psi, args);
     launched(c);
+}
+
+// U0/T0: unroll and block size of the 128-bit variant
+template <int K, int U0, int T0>
+static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
+                         const double* m_host) {
+    static DenseArgs<K> args;  // staging for the parameter block (copied by the launch)
+    const bool bit0_target = tpos[0] == 0;
+    if (bit0_target) {
+        fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host);
+        launch_dense_mode<K, 1, 1, (K >= 5 ? 128 : 256), (K == 3 ? 2 : (K <= 2 ? 4 : 3))>(c, psi, args);
+    } else {
+        fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host);
+        launch_dense_mode<K, 0, U0, T0, (K == 3 ? 2 : (K <= 2 ? 3 : 3))>(c, psi, args);
+    }
 }
 
 void apply_dense(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,

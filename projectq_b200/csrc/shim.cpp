@@ -324,7 +324,7 @@ PYBIND11_MODULE(_pqb_shim, m) {
     });
     py::class_<Simulator>(m, "Simulator")
         .def(py::init<uint32_t, int, int, int, int, py::object, int>(), py::arg("seed") = 1, py::arg("device") = 0,
-             py::arg("fusion_max_qubits") = 5, py::arg("rank") = 0, py::arg("world_size") = 1,
+             py::arg("fusion_max_qubits") = 0, py::arg("rank") = 0, py::arg("world_size") = 1,
              py::arg("nccl_unique_id") = py::none(), py::arg("reserve_qubits") = 0)
         .def("allocate_qubit", &Simulator::allocate_qubit)
         .def("deallocate_qubit", &Simulator::deallocate_qubit)
