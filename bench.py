@@ -209,6 +209,7 @@ def main():
 
     def step_packed():
         sim.apply_gate_stream(body, n_gates, True)
+        sim.run()  # every step is self-contained: nothing stays queued past the timed region
 
     for _ in range(warmup):
         step_packed()

@@ -157,7 +157,7 @@ class Simulator(BasicEngine):
                     f"Simulator: Error applying {str(gate)} gate: {int(math.log(len(matrix), 2))}-qubit"
                     f" gate applied to {len(ids)} qubits."
                 )
-            self._simulator.apply_controlled_gate(matrix, ids, _ids(cmd.control_qubits))
+            self._simulator.apply_controlled_gate(matrix.tolist(), ids, _ids(cmd.control_qubits))
             if not self._gate_fusion:
                 self._simulator.run()
         else:

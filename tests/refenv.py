@@ -47,5 +47,8 @@ def import_projectq():
         spec.loader.exec_module(mod)
         sys.modules["projectq.backends._sim._cppsim"] = mod
     import projectq
+    import projectq.backends._sim as _sim_pkg
 
+    if "projectq.backends._sim._cppsim" in sys.modules:
+        _sim_pkg._cppsim = sys.modules["projectq.backends._sim._cppsim"]
     return projectq
