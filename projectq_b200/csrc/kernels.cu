@@ -78,7 +78,9 @@ static int reduce_grid(uint64_t work_items, int per_block) {
 // ------------------------------------------------------------------------------------------------------------------
 // The 2^k x 2^k matrix travels in the kernel parameter block (constant bank 0, <= 16 KB at k = 5), so with the
 // row/column loops fully unrolled every matrix element is an immediate constant-bank operand of a DFMA — no loads,
-// no shared memory, no separate upload.  One thread owns U amplitude groups: 2^k strided 128-bit loads each, the
+// no shared memory, no separate upload.  (Tried and measured slower on B200, see DESIGN.md: a rolled row loop with the
+// matrix in shared memory, 3.8 ms vs 3.0 ms per k = 5 pass at 28 qubits; Gauss's 3-multiplication complex product, whose
+// extra registers cost more occupancy than the 25 % fewer DFMAs gain.)  One thread owns U amplitude groups: 2^k strided 128-bit loads each, the
 // mat-vec in registers, 2^k 128-bit stores.  Controls are handled by enumerating only the groups whose control bits
 // are set (zero bits are inserted at the control positions and then OR-ed in), so a c-controlled pass touches 2^-c
 // of the state instead of testing and skipping like the reference (kernel2.hpp:60-70).
@@ -178,122 +180,6 @@ __global__ void __launch_bounds__(THREADS, MINB) apply_dense_kernel(double2* __r
     }
 }
 
-// ---- k = 4, 5: three-multiplication complex product -------------------------------------------------------------------
-// At k = 4 the plain mat-vec keeps the FP64 pipe 76 % busy at full clocks while HBM is 84 % busy (ncu, profiles/), and
-// under the sustained power cap (~1.5 GHz) the FP64 pipe becomes the bound; at k = 5 it is the bound outright.  Gauss's
-// trick trades the 4 real FMAs of a complex multiply-add for 3: with m = a + ib and v = x + iy,
-//     T = sum a (x + y),   R = sum (a + b) y,   I = sum (b - a) x,   re = T - R,   im = T + I.
-// The host precomputes (a, a+b, b-a) per matrix element (24 B each, 24 KB at k = 5, still inside the 32 KB parameter
-// block); the thread forms s = x + y once per input.  25 % fewer FP64 instructions, results equal to ~1 ulp of |m||v|.
-template <int K>
-struct GaussArgs {
-    // planar, 16-byte aligned: a = Re m, a + b, b - a (two neighbouring columns load as one 128-bit constant access)
-    alignas(16) double ca[(1 << K) * (1 << K)];
-    alignas(16) double cs[(1 << K) * (1 << K)];
-    alignas(16) double cd[(1 << K) * (1 << K)];
-    uint64_t n_items;
-    uint64_t ctrl_mask;
-    int n_ins;
-    uint8_t tpos[8];
-    uint8_t ins_pos[64];
-};
-
-template <int K, int MODE, int THREADS, int MINB, int RB>
-__global__ void __launch_bounds__(THREADS, MINB) apply_dense_gauss_kernel(double2* __restrict__ psi,
-                                                                    const __grid_constant__ GaussArgs<K> p) {
-    constexpr int D = 1 << K;
-    const uint64_t g = uint64_t(blockIdx.x) * THREADS + threadIdx.x;
-    if (g >= p.n_items) return;
-    uint64_t stride[K];
-#pragma unroll
-    for (int l = 0; l < K; ++l) stride[l] = uint64_t(1) << p.tpos[l];
-    auto offset = [&](int j) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int l = 0; l < K; ++l)
-            if ((j >> l) & 1) off += stride[l];
-        return off;
-    };
-    double2* base = psi + (insert_zero_bits(g, p.ins_pos, p.n_ins) | p.ctrl_mask);
-    double x[D], y[D], s[D];
-    if constexpr (MODE == 1) {
-#pragma unroll
-        for (int j = 0; j < D; j += 2) {
-            double2 a, b;
-            ld256(base + offset(j), a, b);
-            x[j] = a.x; y[j] = a.y; x[j + 1] = b.x; y[j + 1] = b.y;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const double2 a = base[offset(j)];
-            x[j] = a.x; y[j] = a.y;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < D; ++j) s[j] = x[j] + y[j];
-#pragma unroll
-    for (int i0 = 0; i0 < D; i0 += RB) {
-        double T[RB], R[RB], I[RB];
-#pragma unroll
-        for (int r = 0; r < RB; ++r) T[r] = R[r] = I[r] = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-#pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const int e = (i0 + r) * D + j;
-                T[r] = fma(p.ca[e], s[j], T[r]);
-                R[r] = fma(p.cs[e], y[j], R[r]);
-                I[r] = fma(p.cd[e], x[j], I[r]);
-            }
-        }
-        if constexpr (MODE == 1) {
-#pragma unroll
-            for (int r = 0; r < RB; r += 2)
-                st256(base + offset(i0 + r), make_double2(T[r] - R[r], T[r] + I[r]),
-                      make_double2(T[r + 1] - R[r + 1], T[r + 1] + I[r + 1]));
-        } else {
-#pragma unroll
-            for (int r = 0; r < RB; ++r) base[offset(i0 + r)] = make_double2(T[r] - R[r], T[r] + I[r]);
-        }
-    }
-}
-
-template <int K, int THREADS, int MINB, int RB>
-static void launch_dense_gauss(const Ctx& c, double2* psi, int n_bits, const uint8_t* tpos, int n_ctrl,
-                               const uint8_t* cpos, const double* m_host) {
-    constexpr int D = 1 << K;
-    static GaussArgs<K> args;
-    for (int i = 0; i < D * D; ++i) {
-        const double a = m_host[2 * i], b = m_host[2 * i + 1];
-        args.ca[i] = a;
-        args.cs[i] = a + b;
-        args.cd[i] = b - a;
-    }
-    int a = 0, b = 0, n = 0;
-    uint64_t cmask = 0;
-    while (a < K || b < n_ctrl) {
-        if (b >= n_ctrl || (a < K && tpos[a] < cpos[b]))
-            args.ins_pos[n++] = tpos[a++];
-        else {
-            cmask |= uint64_t(1) << cpos[b];
-            args.ins_pos[n++] = cpos[b++];
-        }
-    }
-    args.n_ins = n;
-    args.ctrl_mask = cmask;
-    for (int l = 0; l < K; ++l) args.tpos[l] = tpos[l];
-    if (n > n_bits) throw std::invalid_argument("apply_dense: more target/control bits than state bits");
-    args.n_items = uint64_t(1) << (n_bits - n);
-    const uint64_t blocks = (args.n_items + THREADS - 1) / THREADS;
-    if (blocks > 0x7fffffffULL) throw std::invalid_argument("apply_dense: grid too large");
-    if (tpos[0] == 0)
-        apply_dense_gauss_kernel<K, 1, THREADS, MINB, RB><<<unsigned(blocks), THREADS, 0, c.stream>>>(psi, args);
-    else
-        apply_dense_gauss_kernel<K, 0, THREADS, MINB, RB><<<unsigned(blocks), THREADS, 0, c.stream>>>(psi, args);
-    launched(c);
-}
-
 template <int K>
 static void fill_dense_args(DenseArgs<K>& args, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
                             const double* m_host) {
@@ -347,8 +233,8 @@ void apply_dense(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* t
         case 1: launch_dense<1, 4, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
         case 2: launch_dense<2, 2, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
         case 3: launch_dense<3, 2, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
-        case 4: launch_dense_gauss<4, 256, 2, 4>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
-        case 5: launch_dense_gauss<5, 128, 2, 4>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
+        case 4: launch_dense<4, 1, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
+        case 5: launch_dense<5, 1, 128>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
         default: throw std::invalid_argument("Gates with more than 5 qubits are not supported!");
     }
 }

@@ -38,17 +38,18 @@ struct Terms {
 void pack_terms(const py::object& terms, bool complex_coeff, Terms& out) {
     out.offsets.push_back(0);
     for (auto item : terms) {
-        py::tuple tup = py::reinterpret_borrow<py::tuple>(item);
-        if (tup.size() != 2) throw py::type_error("each term must be a (term, coefficient) pair");
+        py::sequence tup = py::reinterpret_borrow<py::sequence>(item);
+        if (py::len(tup) != 2) throw py::type_error("each term must be a (term, coefficient) pair");
         for (auto op : tup[0]) {
-            py::tuple o = py::reinterpret_borrow<py::tuple>(op);
+            py::sequence o = py::reinterpret_borrow<py::sequence>(op);
+            if (py::len(o) != 2) throw py::type_error("each factor must be an (index, 'X'|'Y'|'Z') pair");
             out.qidx.push_back(o[0].cast<uint32_t>());
             std::string s = o[1].cast<std::string>();
             if (s.size() != 1) throw py::type_error("Pauli action must be a single character");
             out.pauli.push_back(s[0]);
         }
         out.offsets.push_back(out.qidx.size());
-        py::handle c = tup[1];
+        py::object c = tup[1];
         if (complex_coeff) {
             const cplx v = c.cast<cplx>();
             out.coeff.push_back(v.real());

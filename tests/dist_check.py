@@ -1,0 +1,153 @@
+"""Sharded-state parity check, run as one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
+
+Every rank drives the same call sequence (SPMD) on its shard; results are compared with the NumPy oracle computed on every
+rank.  torch.distributed (gloo) is plumbing only: it broadcasts the NCCL id.  Exit code 0 = all checks passed on all ranks.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.statevec_oracle import OracleSimulator  # noqa: E402
+from tests.helpers import brickwork_circuit, rand_state, rand_unitary, tfim_terms  # noqa: E402
+
+TOL = 1e-12
+
+
+def main():
+    import torch.distributed as dist
+
+    from projectq_b200.backend import SimulatorBackend, nccl_unique_id
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    box = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+
+    def make(seed=1, **kw):
+        return SimulatorBackend(seed, device=local, rank=rank, world_size=world, nccl_unique_id=box[0], **kw)
+
+    def same(gpu, chk, what, tol=TOL):
+        m1, v1 = gpu.cheat()
+        m2, v2 = chk.cheat()
+        assert dict(m1) == dict(m2), (what, m1, m2)
+        err = float(np.max(np.abs(np.asarray(v1) - v2)))
+        assert err < tol, (what, err)
+        return err
+
+    rng = np.random.default_rng(99)  # same stream on every rank
+
+    # 1. allocate one by one (the first log2(world) qubits land on rank bits), gates on every qubit -> remaps
+    n = 12
+    gpu, chk = make(3), OracleSimulator(3)
+    for q in range(n):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+        m = rand_unitary(rng, 1)
+        gpu.apply_controlled_gate(m, [q], [q - 1] if q else [])
+        chk.apply_controlled_gate(m, [q], [q - 1] if q else [])
+    same(gpu, chk, "allocate+gates")
+    for g in range(80):
+        k = int(rng.integers(1, 5))
+        nc = int(rng.integers(0, 3))
+        qs = [int(x) for x in rng.permutation(n)[: k + nc]]
+        m = rand_unitary(rng, k) if rng.random() < 0.8 else np.diag(np.exp(1j * rng.uniform(0, 6.28, 1 << k)))
+        gpu.apply_controlled_gate(m, qs[:k], qs[k:])
+        chk.apply_controlled_gate(m, qs[:k], qs[k:])
+        if g % 9 == 0:
+            gpu.run()
+    same(gpu, chk, "random circuit")
+    st = gpu.stats()
+    assert st["remaps"] > 0, st
+
+    # 2. queries
+    for _ in range(6):
+        k = int(rng.integers(1, 5))
+        sub = [int(x) for x in rng.permutation(n)[:k]]
+        bits = [bool(b) for b in rng.integers(0, 2, k)]
+        assert abs(gpu.get_probability(bits, sub) - chk.get_probability(bits, sub)) < TOL
+        full = [int(x) for x in rng.permutation(n)]
+        fb = [bool(b) for b in rng.integers(0, 2, n)]
+        assert abs(gpu.get_amplitude(fb, full) - chk.get_amplitude(fb, full)) < TOL
+    terms = tfim_terms(n) + [([(0, "Y"), (3, "X"), (11, "Z")], 0.37), ([], 0.25), ([(1, "Y"), (10, "Y")], -1.1)]
+    ids = [int(x) for x in rng.permutation(n)]
+    e1, e2 = gpu.get_expectation_value(terms, ids), chk.get_expectation_value(terms, ids)
+    assert abs(e1 - e2) < 1e-11, (e1, e2)
+
+    # 3. time evolution (controlled) and apply_qubit_operator
+    gpu.emulate_time_evolution(tfim_terms(n - 1), 0.4, list(range(n - 1)), [n - 1])
+    chk.emulate_time_evolution(tfim_terms(n - 1), 0.4, list(range(n - 1)), [n - 1])
+    same(gpu, chk, "time evolution")
+    cterms = [(t, c * (1 + 0.5j)) for t, c in terms]
+    gpu.apply_qubit_operator(cterms, ids)
+    chk.apply_qubit_operator(cterms, ids)
+    same(gpu, chk, "apply_qubit_operator", tol=1e-10)
+    nrm = float(np.linalg.norm(chk.cheat()[1]))
+    wf = chk.cheat()[1] / nrm
+    order = [int(x) for x in rng.permutation(n)]
+    back = {v: k for k, v in chk.cheat()[0].items()}
+    cur_order = [back[p] for p in range(n)]
+    gpu.set_wavefunction(wf, cur_order)
+    chk.set_wavefunction(wf, cur_order)
+    same(gpu, chk, "set_wavefunction")
+    del order
+
+    # 4. emulate_math (bit-exact on identical inputs)
+    gpu.emulate_math_addConstant(5, [[0, 1, 2, 3, 4]], [11])
+    chk.emulate_math_addConstant(5, [[0, 1, 2, 3, 4]], [11])
+    gpu.emulate_math_multiplyByConstantModN(3, 32, [[5, 6, 7, 8, 9]], [])
+    chk.emulate_math_multiplyByConstantModN(3, 32, [[5, 6, 7, 8, 9]], [])
+    m1, v1 = gpu.cheat()
+    assert np.array_equal(np.asarray(v1), chk.cheat()[1]), "emulate_math not bit-exact"
+
+    # 5. measurement (same RNG stream), collapse, deallocation incl. qubits on rank bits
+    for mids in ([3], [0, 5], [7, 1, 2]):
+        a, b = list(gpu.measure_qubits(mids)), list(chk.measure_qubits(mids))
+        assert a == b, (mids, a, b)
+    same(gpu, chk, "measure")
+    for q in (3, 0, 5, 2, 1, 7):
+        assert gpu.is_classical(q) == chk.is_classical(q)
+        gpu.deallocate_qubit(q)
+        chk.deallocate_qubit(q)
+        same(gpu, chk, "deallocate %d" % q)
+    gpu.collapse_wavefunction([4, 6], [True, False]) if chk.get_probability([True, False], [4, 6]) > 1e-6 else None
+    if chk.get_probability([True, False], [4, 6]) > 1e-6:
+        chk.collapse_wavefunction([4, 6], [True, False])
+    same(gpu, chk, "collapse")
+    gpu.allocate_qubit(50)
+    chk.allocate_qubit(50)
+    m = rand_unitary(rng, 2)
+    gpu.apply_controlled_gate(m, [50, 4], [])
+    chk.apply_controlled_gate(m, [50, 4], [])
+    same(gpu, chk, "re-allocate")
+    del gpu
+
+    # 6. a wider state: fused brickwork on 20 qubits vs the oracle
+    n = 20
+    gates = brickwork_circuit(n, 3, seed=8)
+    gpu, chk = make(1), OracleSimulator(1)
+    wf = rand_state(rng, n)
+    for q in range(n):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    gpu.set_wavefunction(wf, list(range(n)))
+    chk.set_wavefunction(wf, list(range(n)))
+    for m, t, c in gates:
+        gpu.apply_controlled_gate(m, t, c)
+        chk.apply_controlled_gate(m, t, c)
+    err = same(gpu, chk, "brickwork 20q")
+    st = gpu.stats()
+    if rank == 0:
+        print("dist_check OK: world=%d, brickwork max|dpsi|=%.2e, stats=%s" % (world, err, st), flush=True)
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    main()
