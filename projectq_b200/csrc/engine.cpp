@@ -869,43 +869,66 @@ static void to_physical(std::vector<k::PauliTerm>& terms, const std::vector<uint
 
 double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, size_t n_ids) {
     run();
-    auto terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);
-    if (dist_) {
-        std::vector<uint32_t> need;
-        for (auto& tm : terms)
-            for (int p = 0; p < n_; ++p)
-                if ((tm.xmask >> p) & 1) need.push_back(uint32_t(p));
-        std::sort(need.begin(), need.end());
-        need.erase(std::unique(need.begin(), need.end()), need.end());
-        make_local(need);
-    }
-    to_physical(terms, loc_, n_, rank_);
-    std::stable_sort(terms.begin(), terms.end(),
-                     [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+    auto all_terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);  // logical masks
     double* d_acc = d_scalars_;
     PQB_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double), stream_));
-    size_t i = 0;
-    while (i < terms.size()) {
-        size_t j = i;
-        while (j < terms.size() && terms[j].xmask == terms[i].xmask && j - i < 64) ++j;
-        k::pauli_expectation_group(ctx(), psi(), L_, terms[i].xmask, &terms[i], int(j - i), d_partials_, d_acc);
-        i = j;
+    // In a sharded run the X-support of a term must sit on local bits.  Terms are taken in batches whose combined
+    // X-support fits on the device; each batch costs at most one remap of the state (nothing else has to move because
+    // the expectation value is read-only and additive).  On one GPU this is a single batch.
+    std::vector<char> done(all_terms.size(), 0);
+    size_t left = all_terms.size();
+    while (left > 0) {
+        std::vector<k::PauliTerm> batch;
+        uint64_t need_mask = 0;
+        for (size_t i = 0; i < all_terms.size(); ++i) {
+            if (done[i]) continue;
+            const uint64_t merged = need_mask | all_terms[i].xmask;
+            if (dist_ && __builtin_popcountll(merged) > L_) continue;
+            need_mask = merged;
+            batch.push_back(all_terms[i]);
+            done[i] = 1;
+            --left;
+        }
+        if (batch.empty()) throw RuntimeErr("get_expectation_value(): a term flips more qubits than one shard holds");
+        if (dist_) {
+            std::vector<uint32_t> need;
+            for (int p = 0; p < n_; ++p)
+                if ((need_mask >> p) & 1) need.push_back(uint32_t(p));
+            make_local(need);
+        }
+        to_physical(batch, loc_, n_, rank_);
+        std::stable_sort(batch.begin(), batch.end(),
+                         [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+        const bool active = !dist_ || (uint64_t(rank_) & dist_->free_rank_bits_mask()) == 0;
+        size_t i = 0;
+        while (active && i < batch.size()) {
+            size_t j = i;
+            while (j < batch.size() && batch[j].xmask == batch[i].xmask && j - i < 64) ++j;
+            k::pauli_expectation_group(ctx(), psi(), L_, batch[i].xmask, &batch[i], int(j - i), d_partials_, d_acc);
+            i = j;
+        }
     }
     return allreduce_sum(read_scalar(d_acc));
+}
+
+// X-support of a term list as logical positions; in a sharded run it has to fit on the local bits all at once because
+// the out-of-place vectors of apply_qubit_operator / emulate_time_evolution are not re-laid-out between terms.
+static std::vector<uint32_t> x_support(const std::vector<k::PauliTerm>& terms, int n, int local_bits, const char* who) {
+    uint64_t m = 0;
+    for (auto& tm : terms) m |= tm.xmask;
+    std::vector<uint32_t> need;
+    for (int p = 0; p < n; ++p)
+        if ((m >> p) & 1) need.push_back(uint32_t(p));
+    if (int(need.size()) > local_bits)
+        throw RuntimeErr(std::string(who) + ": in a sharded run the X/Y terms of the operator may touch at most as many "
+                         "qubits as one shard holds (" + std::to_string(local_bits) + ")");
+    return need;
 }
 
 void Engine::apply_qubit_operator(const TermsView& t, const uint32_t* ids, size_t n_ids) {
     run();
     auto terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);
-    if (dist_) {
-        std::vector<uint32_t> need;
-        for (auto& tm : terms)
-            for (int p = 0; p < n_; ++p)
-                if ((tm.xmask >> p) & 1) need.push_back(uint32_t(p));
-        std::sort(need.begin(), need.end());
-        need.erase(std::unique(need.begin(), need.end()), need.end());
-        make_local(need);
-    }
+    if (dist_) make_local(x_support(terms, n_, L_, "apply_qubit_operator()"));
     to_physical(terms, loc_, n_, rank_);
     std::stable_sort(terms.begin(), terms.end(),
                      [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
@@ -931,15 +954,7 @@ void Engine::emulate_time_evolution(const TermsView& t, double time, const uint3
     const std::complex<double> correction = std::exp(std::complex<double>(0.0, -time * tr / double(s)));
     std::vector<uint32_t> cl;
     for (size_t i = 0; i < nc; ++i) cl.push_back(pos_of(ctrl[i], "emulate_time_evolution(): Unknown control qubit id."));
-    if (dist_) {
-        std::vector<uint32_t> need;
-        for (auto& tm : terms)
-            for (int p = 0; p < n_; ++p)
-                if ((tm.xmask >> p) & 1) need.push_back(uint32_t(p));
-        std::sort(need.begin(), need.end());
-        need.erase(std::unique(need.begin(), need.end()), need.end());
-        make_local(need);
-    }
+    if (dist_) make_local(x_support(terms, n_, L_, "emulate_time_evolution()"));
     to_physical(terms, loc_, n_, rank_);
     std::stable_sort(terms.begin(), terms.end(),
                      [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });

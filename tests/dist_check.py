@@ -28,10 +28,10 @@ def main():
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    box = [nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
 
     def make(seed=1, **kw):
+        box = [nccl_unique_id() if rank == 0 else None]  # one fresh NCCL id per communicator
+        dist.broadcast_object_list(box, src=0)
         return SimulatorBackend(seed, device=local, rank=rank, world_size=world, nccl_unique_id=box[0], **kw)
 
     def same(gpu, chk, what, tol=TOL):
@@ -82,9 +82,13 @@ def main():
     assert abs(e1 - e2) < 1e-11, (e1, e2)
 
     # 3. time evolution (controlled) and apply_qubit_operator
-    gpu.emulate_time_evolution(tfim_terms(n - 1), 0.4, list(range(n - 1)), [n - 1])
-    chk.emulate_time_evolution(tfim_terms(n - 1), 0.4, list(range(n - 1)), [n - 1])
+    # X/Y support of the operator must fit on one shard (n - log2(world) qubits); Z terms may touch every qubit
+    nl = n - int(np.log2(world))
+    hterms = tfim_terms(nl - 1) + [([(i, "Z"), (n - 2, "Z")], 0.3) for i in range(3)] + [([], 0.2)]
+    gpu.emulate_time_evolution(hterms, 0.4, list(range(n - 1)), [n - 1])
+    chk.emulate_time_evolution(hterms, 0.4, list(range(n - 1)), [n - 1])
     same(gpu, chk, "time evolution")
+    terms = hterms + [([(0, "Y"), (3, "X"), (11, "Z")], 0.37), ([(1, "Y"), (2, "Y")], -1.1)]
     cterms = [(t, c * (1 + 0.5j)) for t, c in terms]
     gpu.apply_qubit_operator(cterms, ids)
     chk.apply_qubit_operator(cterms, ids)
