@@ -62,7 +62,7 @@ void cuda_check(cudaError_t e, const char* what) {
 }  // namespace
 
 std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_local_bits,
-                                            const std::vector<uint32_t>& need) {
+                                            const std::vector<uint32_t>& need, const std::vector<uint32_t>* victims) {
     std::vector<std::pair<int, int>> swaps;
     std::vector<uint32_t> global_needed;
     for (auto lp : need) {
@@ -71,20 +71,27 @@ std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_loc
             global_needed.push_back(lp);
     }
     if (global_needed.empty()) return swaps;
-    // owner of each local bit
-    std::vector<int> owner(n_local_bits, -1);
-    for (size_t p = 0; p < loc.size(); ++p)
-        if (loc[p] < 64) owner[loc[p]] = int(p);
-    int b = n_local_bits - 1;
-    for (auto lp : global_needed) {
-        while (b >= 0 && owner[b] >= 0 && std::find(need.begin(), need.end(), uint32_t(owner[b])) != need.end()) --b;
-        if (b < 0) throw std::runtime_error("remap: not enough local qubits to bring every target of the gate on-device");
-        const int r = loc[lp] - 64;
+    auto needed = [&](uint32_t lp) { return std::find(need.begin(), need.end(), lp) != need.end(); };
+    // eviction candidates: the caller's preference order, else the highest local bits (largest contiguous blocks)
+    std::vector<uint32_t> order;
+    if (victims) {
+        for (auto lp : *victims)
+            if (lp < loc.size() && loc[lp] < 64 && !needed(lp)) order.push_back(lp);
+    } else {
+        std::vector<int> owner(n_local_bits, -1);
+        for (size_t p = 0; p < loc.size(); ++p)
+            if (loc[p] < 64) owner[loc[p]] = int(p);
+        for (int b = n_local_bits - 1; b >= 0; --b)
+            if (owner[b] >= 0 && !needed(uint32_t(owner[b]))) order.push_back(uint32_t(owner[b]));
+    }
+    if (order.size() < global_needed.size())
+        throw std::runtime_error("remap: not enough local qubits to bring every target of the gate on-device");
+    for (size_t i = 0; i < global_needed.size(); ++i) {
+        const uint32_t in = global_needed[i], out = order[i];
+        const int r = loc[in] - 64, b = loc[out];
         swaps.emplace_back(r, b);
-        if (owner[b] >= 0) loc[owner[b]] = uint8_t(64 + r);
-        loc[lp] = uint8_t(b);
-        owner[b] = int(lp);
-        --b;
+        loc[out] = uint8_t(64 + r);
+        loc[in] = uint8_t(b);
     }
     return swaps;
 }

@@ -17,7 +17,9 @@ namespace pqb {
 // loc[p] = placement of logical position p: local bit (< 64) or 64 + rank bit.  `need` lists logical positions that must
 // become local.  Returns the (rank bit, local bit) pairs to exchange, choosing the highest local bits not in `need`
 // (their halves are the largest contiguous blocks), and updates loc.  Throws std::runtime_error if it cannot be done.
-std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_local_bits, const std::vector<uint32_t>& need);
+// `victims` (optional) lists logical positions in eviction-preference order (the engine passes "needed last" first).
+std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_local_bits, const std::vector<uint32_t>& need,
+                                            const std::vector<uint32_t>* victims = nullptr);
 
 class Dist {
 public:

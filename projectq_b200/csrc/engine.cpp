@@ -358,7 +358,7 @@ void Engine::apply_pass(const FusedPass& p) {
 }
 
 // bring the given logical positions onto local bits (global<->local qubit remap over NVLink)
-void Engine::make_local(const std::vector<uint32_t>& need) {
+void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uint32_t>* victims) {
     if (!dist_) return;
     bool any = false;
     for (auto lp : need)
@@ -366,7 +366,7 @@ void Engine::make_local(const std::vector<uint32_t>& need) {
     if (!any) return;
     std::vector<std::pair<int, int>> swaps;
     try {
-        swaps = plan_remap(loc_, L_, need);
+        swaps = plan_remap(loc_, L_, need, victims);
     } catch (const std::runtime_error& e) {
         throw RuntimeErr(e.what());
     }
@@ -397,6 +397,10 @@ void Engine::make_local(const std::vector<uint32_t>& need) {
 
 void Engine::run() {
     if (fuser_.pending() == 0) return;
+    if (dist_) {
+        run_sharded();
+        return;
+    }
     // every id must be known before positions are resolved (the reference would silently insert into map_)
     // sort key of a qubit inside a pass = its physical place; rank bits sort above all local bits
     auto key = [this](uint32_t id) -> uint64_t {
@@ -432,16 +436,48 @@ void Engine::run() {
         fuser_.clear();  // never leave a poisoned queue behind (the reference does, simulator.hpp:522-526)
         throw;
     }
-    for (auto& p : passes) {
-        if (dist_) {
+    for (auto& p : passes) apply_pass(p);
+}
+
+// Sharded run(): execute everything that touches only on-device qubits, and only then pay for a remap.  The remap brings
+// in the rank-bit qubits of the oldest waiting gate and evicts the local qubits that are needed last (Belady), so a
+// brickwork circuit needs about one remap per global qubit per flush instead of one per layer.
+void Engine::run_sharded() {
+    auto key = [this](uint32_t id) -> uint64_t {
+        auto it = map_.find(id);
+        if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
+        return loc_[it->second];
+    };
+    auto blocked = [this](uint32_t id) -> bool {
+        auto it = map_.find(id);
+        if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
+        return loc_[it->second] >= 64;
+    };
+    const int width = fusion_max_ > 0 ? fusion_max_ : 4;
+    try {
+        while (fuser_.pending() > 0) {
+            std::vector<FusedPass> passes = fuser_.drain_unblocked(width, key, blocked);
+            for (auto& p : passes) apply_pass(p);
+            if (fuser_.pending() == 0) break;
+            // the oldest waiting gate has no unfinished predecessor, so it waits for one of its own qubits
+            const Gate& g = fuser_.pending_gate(0);
             std::vector<uint32_t> need;
-            if (!p.diagonal)
-                for (auto t : p.targets) need.push_back(map_.at(t));
-            make_local(need);
-            // the remap may have moved targets: put the matrix bits back in ascending physical order
-            if (!p.diagonal) Fuser::reorder(p, key);
+            for (auto t : g.targets) need.push_back(map_.at(t));
+            for (auto c : g.ctrls) need.push_back(map_.at(c));
+            std::vector<std::pair<size_t, uint32_t>> use;  // (next use, logical position) of every local qubit
+            for (auto& kv : map_)
+                if (is_local(kv.second)) use.emplace_back(fuser_.next_use(kv.first), kv.second);
+            std::sort(use.begin(), use.end(), [this](const std::pair<size_t, uint32_t>& a, const std::pair<size_t, uint32_t>& b) {
+                if (a.first != b.first) return a.first > b.first;  // needed last (or never: size_t(-1)) first
+                return loc_[a.second] > loc_[b.second];            // then the highest bit: largest contiguous blocks
+            });
+            std::vector<uint32_t> victims;
+            for (auto& u : use) victims.push_back(u.second);
+            make_local(need, &victims);
         }
-        apply_pass(p);
+    } catch (...) {
+        fuser_.clear();
+        throw;
     }
 }
 

@@ -105,8 +105,9 @@ private:
     void swap_state(GrowBuffer*& other);
     std::vector<k::PauliTerm> build_terms(const TermsView& t, const uint32_t* ids, size_t n_ids, bool skip_identity,
                                           double* identity_sum_re, double* identity_sum_im);
-    void make_local(const std::vector<uint32_t>& logical_positions);
+    void make_local(const std::vector<uint32_t>& logical_positions, const std::vector<uint32_t>* victims = nullptr);
     void apply_pass(const FusedPass& p);
+    void run_sharded();
     unsigned long long last_probe_[2] = {~0ULL, ~0ULL};  // result of the last classical probe (bit 0, bit 1)
     double draw_uniform();
 

@@ -166,9 +166,43 @@ std::vector<FusedPass> Fuser::drain(int max_qubits, const std::function<uint64_t
 }
 
 std::vector<FusedPass> Fuser::plan(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key) const {
+    std::vector<char> done;
+    return plan_impl(max_qubits, sort_key, nullptr, done);
+}
+
+std::vector<FusedPass> Fuser::drain_unblocked(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key,
+                                              const std::function<bool(uint32_t)>& blocked) {
+    std::vector<char> done;
+    std::vector<FusedPass> passes = plan_impl(max_qubits, sort_key, &blocked, done);
+    std::vector<Gate> rest;
+    for (size_t g = 0; g < pending_.size(); ++g)
+        if (!done[g]) rest.push_back(std::move(pending_[g]));
+    pending_.swap(rest);
+    return passes;
+}
+
+size_t Fuser::next_use(uint32_t id) const {
+    for (size_t g = 0; g < pending_.size(); ++g) {
+        if (contains(pending_[g].targets, id) || contains(pending_[g].ctrls, id)) return g;
+    }
+    return size_t(-1);
+}
+
+std::vector<FusedPass> Fuser::plan_impl(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key,
+                                        const std::function<bool(uint32_t)>* blocked, std::vector<char>& done) const {
     std::vector<FusedPass> passes;
     const size_t m = pending_.size();
+    done.assign(m, 0);
     if (m == 0) return passes;
+    // gates that touch a blocked qubit (one that sits on a rank bit of the sharded state) are left for later
+    std::vector<char> is_blocked(m, 0);
+    if (blocked)
+        for (size_t g = 0; g < m; ++g) {
+            for (auto t : pending_[g].targets)
+                if ((*blocked)(t)) is_blocked[g] = 1;
+            for (auto c : pending_[g].ctrls)
+                if ((*blocked)(c)) is_blocked[g] = 1;
+        }
 
     // per-qubit ordered lists of the gates touching it (targets and controls both order gates)
     std::unordered_map<uint32_t, uint32_t> dense;
@@ -191,7 +225,6 @@ std::vector<FusedPass> Fuser::plan(int max_qubits, const std::function<uint64_t(
         for (auto c : pending_[g].ctrls) reg(c);
     }
     std::vector<size_t> head(touch.size(), 0);
-    std::vector<char> done(m, 0);
     auto ready = [&](size_t g) {
         for (auto d : gq[g]) {
             size_t& h = head[d];
@@ -207,20 +240,31 @@ std::vector<FusedPass> Fuser::plan(int max_qubits, const std::function<uint64_t(
     while (true) {
         while (first < m && done[first]) ++first;
         if (first >= m) break;
+        // seed = oldest gate that can run now (with blocked qubits around, not necessarily the oldest pending one)
+        size_t seed = first;
+        if (blocked) {
+            seed = m;
+            for (size_t g = first; g < m; ++g)
+                if (!done[g] && !is_blocked[g] && ready(g)) {
+                    seed = g;
+                    break;
+                }
+            if (seed == m) break;  // everything left waits for a blocked qubit
+        }
         members.clear();
         S.clear();
         G.clear();
-        absorb(S, G, pending_[first], true);
-        members.push_back(&pending_[first]);
-        done[first] = 1;
+        absorb(S, G, pending_[seed], true);
+        members.push_back(&pending_[seed]);
+        done[seed] = 1;
         // grow the pass: prefer gates that fit without widening it, then the smallest widening, then program order
         while (true) {
-            const size_t limit = std::min(m, first + kLookahead);
+            const size_t limit = std::min(m, seed + kLookahead);
             size_t best = m;
             int best_w = max_qubits + 1;
             const int cur_w = int(S.size());
             for (size_t g = first + 1; g < limit; ++g) {
-                if (done[g] || !ready(g)) continue;
+                if (done[g] || is_blocked[g] || !ready(g)) continue;
                 const int w = width_after(S, G, pending_[g]);
                 if (w > max_qubits) continue;
                 if (w < best_w) {

@@ -43,6 +43,15 @@ public:
     // Same schedule, but the pending gates stay queued (used to compare fusion widths before committing to one).
     std::vector<FusedPass> plan(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key) const;
 
+    // Sharded runs: schedule (and remove from the queue) only what can run without touching a blocked qubit; gates that
+    // touch one, and everything that depends on them, stay queued in program order.
+    std::vector<FusedPass> drain_unblocked(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key,
+                                           const std::function<bool(uint32_t)>& blocked);
+    // index of the first pending gate that touches qubit `id` (size_t(-1) if none): the remap planner evicts the local
+    // qubit that is needed last
+    size_t next_use(uint32_t id) const;
+    const Gate& pending_gate(size_t i) const { return pending_[i]; }
+
     // Fuse an explicit list of gates (already chosen to fit) into one pass.
     static FusedPass fuse(const std::vector<const Gate*>& gates, const std::function<uint64_t(uint32_t)>& sort_key);
 
@@ -50,6 +59,8 @@ public:
     static void reorder(FusedPass& p, const std::function<uint64_t(uint32_t)>& sort_key);
 
 private:
+    std::vector<FusedPass> plan_impl(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key,
+                                     const std::function<bool(uint32_t)>* blocked, std::vector<char>& done) const;
     std::vector<Gate> pending_;
 };
 
