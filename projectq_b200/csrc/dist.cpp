@@ -113,11 +113,22 @@ Dist::Dist(int rank, int world, const void* uid, cudaStream_t stream) : rank_(ra
     nccl_check(nccl().CommInitRank(&comm, world_, id, rank_), "ncclCommInitRank");
     comm_ = comm;
     ensure_buf(4096);
+    cuda_check(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+    for (int i = 0; i < 2; ++i) {
+        cuda_check(cudaEventCreateWithFlags(&received_[i], cudaEventDisableTiming), "cudaEventCreate");
+        cuda_check(cudaEventCreateWithFlags(&copied_[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
 }
 
 Dist::~Dist() {
+    if (copy_stream_) cudaStreamSynchronize(copy_stream_);
     if (comm_) nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
     if (d_buf_) cudaFree(d_buf_);
+    for (int i = 0; i < 2; ++i) {
+        if (received_[i]) cudaEventDestroy(received_[i]);
+        if (copied_[i]) cudaEventDestroy(copied_[i]);
+    }
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
 }
 
 void Dist::ensure_buf(size_t n) {
@@ -199,37 +210,35 @@ void Dist::swap_bits(int r, int b, double2* shard, int n_local_bits, double2* st
     const uint64_t n_blocks = uint64_t(1) << (n_local_bits - 1 - b);
     ncclComm_t comm = static_cast<ncclComm_t>(comm_);
     if (staging_amps == 0) throw std::runtime_error("swap_bits: no staging memory");
-    const uint64_t piece = std::min<uint64_t>(block, staging_amps);  // amplitudes per send/recv call
-    // gather as many pieces as fit into the staging area per round, then copy them into place
-    const uint64_t pieces_per_round = std::max<uint64_t>(1, staging_amps / piece);
-    uint64_t in_round = 0;
-    struct Pending {
-        uint64_t off, cnt, soff;
-    };
-    std::vector<Pending> pending;
-    auto flush = [&]() {
-        for (auto& q : pending)
-            cuda_check(cudaMemcpyAsync(shard + q.off, staging + q.soff, q.cnt * sizeof(double2), cudaMemcpyDeviceToDevice,
-                                       stream_),
-                       "staging copy");
-        pending.clear();
-        in_round = 0;
-    };
+    // The half-shard that leaves and the half-shard that arrives occupy the same addresses, so arrivals land in a
+    // staging slot first.  Two slots alternate: while NCCL moves piece i over NVLink on the main stream, the copy of
+    // piece i-1 from its slot into place runs on a side stream, which hides the copies behind the transfers.
+    const uint64_t slot_amps = staging_amps >= 2 ? staging_amps / 2 : staging_amps;
+    const int n_slots = staging_amps >= 2 ? 2 : 1;
+    const uint64_t piece = std::min<uint64_t>(block, slot_amps);
+    uint64_t i = 0;
     for (uint64_t j = 0; j < n_blocks; ++j) {
         const uint64_t start = (j << (b + 1)) | (send_bit << b);
-        for (uint64_t o = 0; o < block; o += piece) {
+        for (uint64_t o = 0; o < block; o += piece, ++i) {
             const uint64_t cnt = std::min(piece, block - o);
-            const uint64_t soff = in_round * piece;
+            const int slot = int(i % n_slots);
+            double2* landing = staging + uint64_t(slot) * slot_amps;
+            if (i >= uint64_t(n_slots)) cuda_check(cudaStreamWaitEvent(stream_, copied_[slot], 0), "wait(copied)");
             nccl_check(nccl().GroupStart(), "ncclGroupStart");
             nccl_check(nccl().Send(shard + start + o, 2 * cnt, ncclDouble, partner, comm, stream_), "ncclSend");
-            nccl_check(nccl().Recv(staging + soff, 2 * cnt, ncclDouble, partner, comm, stream_), "ncclRecv");
+            nccl_check(nccl().Recv(landing, 2 * cnt, ncclDouble, partner, comm, stream_), "ncclRecv");
             nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
-            pending.push_back({start + o, cnt, soff});
+            cuda_check(cudaEventRecord(received_[slot], stream_), "record(received)");
+            cuda_check(cudaStreamWaitEvent(copy_stream_, received_[slot], 0), "wait(received)");
+            cuda_check(cudaMemcpyAsync(shard + start + o, landing, cnt * sizeof(double2), cudaMemcpyDeviceToDevice,
+                                       copy_stream_),
+                       "staging copy");
+            cuda_check(cudaEventRecord(copied_[slot], copy_stream_), "record(copied)");
             if (bytes_sent) *bytes_sent += cnt * sizeof(double2);
-            if (++in_round >= pieces_per_round) flush();
         }
     }
-    flush();
+    for (int slot = 0; slot < n_slots && uint64_t(slot) < i; ++slot)
+        cuda_check(cudaStreamWaitEvent(stream_, copied_[slot], 0), "wait(copied, final)");
 }
 
 }  // namespace pqb
