@@ -273,7 +273,7 @@ def main():
                    "qubits": n, "gates": n_gates, "fused_passes_per_step": n_pass, "pass_width_histogram": passes,
                    "diag_passes": st["diag_passes"], "l2": "state (%.1f GiB per GPU) is far larger than the 126 MB L2"
                    % (16.0 * local_amps / 2**30), "parallelism": "state sharded by the top %d qubits" % int(np.log2(world)),
-                   "norm_after": norm, "p0": p0},
+                   "norm_after": norm, "p0": p0, "sec_per_layer": ms_per_step * 1e-3 / DEPTH},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
                      "kernel": "apply_dense_kernel<k=%d>" % dom_k, "avg_launch_ms": launch_ms,
