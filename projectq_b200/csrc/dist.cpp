@@ -1,5 +1,6 @@
 // Sharded state communicator — see dist.h.
 #include "dist.h"
+#include "kernels.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -117,7 +118,9 @@ Dist::Dist(int rank, int world, const void* uid, cudaStream_t stream) : rank_(ra
     for (int i = 0; i < 2; ++i) {
         cuda_check(cudaEventCreateWithFlags(&received_[i], cudaEventDisableTiming), "cudaEventCreate");
         cuda_check(cudaEventCreateWithFlags(&copied_[i], cudaEventDisableTiming), "cudaEventCreate");
+        cuda_check(cudaEventCreateWithFlags(&packed_[i], cudaEventDisableTiming), "cudaEventCreate");
     }
+    cuda_check(cudaEventCreateWithFlags(&ready_, cudaEventDisableTiming), "cudaEventCreate");
 }
 
 Dist::~Dist() {
@@ -127,7 +130,9 @@ Dist::~Dist() {
     for (int i = 0; i < 2; ++i) {
         if (received_[i]) cudaEventDestroy(received_[i]);
         if (copied_[i]) cudaEventDestroy(copied_[i]);
+        if (packed_[i]) cudaEventDestroy(packed_[i]);
     }
+    if (ready_) cudaEventDestroy(ready_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
 }
 
@@ -210,9 +215,43 @@ void Dist::swap_bits(int r, int b, double2* shard, int n_local_bits, double2* st
     const uint64_t n_blocks = uint64_t(1) << (n_local_bits - 1 - b);
     ncclComm_t comm = static_cast<ncclComm_t>(comm_);
     if (staging_amps == 0) throw std::runtime_error("swap_bits: no staging memory");
+    cuda_check(cudaEventRecord(ready_, stream_), "record(ready)");  // everything queued so far precedes the side stream
     // The half-shard that leaves and the half-shard that arrives occupy the same addresses, so arrivals land in a
     // staging slot first.  Two slots alternate: while NCCL moves piece i over NVLink on the main stream, the copy of
     // piece i-1 from its slot into place runs on a side stream, which hides the copies behind the transfers.
+    if (block < (uint64_t(1) << 20) && staging_amps >= 4) {
+        // Low local bit: the half is scattered in runs shorter than 16 MiB, far too many messages for NCCL (measured
+        // 38 GB/s at b ~ 0 on a 128 GiB shard).  Gather each piece into a contiguous slot, exchange the slots, scatter the
+        // arrival back.  Four slots (out/in x 2) so that packing piece i+1 and unpacking piece i-1 overlap the transfer.
+        const uint64_t half_amps = uint64_t(1) << (n_local_bits - 1);
+        const uint64_t slot = staging_amps / 4;
+        uint64_t i = 0;
+        for (uint64_t first = 0; first < half_amps; first += slot, ++i) {
+            const uint64_t cnt = std::min(slot, half_amps - first);
+            const int sl = int(i % 2);
+            double2* out = staging + uint64_t(sl) * slot;
+            double2* in = staging + uint64_t(2 + sl) * slot;
+            // the side stream packs piece i as soon as slot `sl` has been drained by the send of piece i-2
+            if (i >= 2) cuda_check(cudaStreamWaitEvent(copy_stream_, received_[sl], 0), "wait(sent)");
+            else cuda_check(cudaStreamWaitEvent(copy_stream_, ready_, 0), "wait(ready)");
+            k::pack_half(copy_stream_, shard, out, first, cnt, b, int(send_bit));
+            cuda_check(cudaEventRecord(packed_[sl], copy_stream_), "record(packed)");
+            cuda_check(cudaStreamWaitEvent(stream_, packed_[sl], 0), "wait(packed)");
+            if (i >= 2) cuda_check(cudaStreamWaitEvent(stream_, copied_[sl], 0), "wait(unpacked)");
+            nccl_check(nccl().GroupStart(), "ncclGroupStart");
+            nccl_check(nccl().Send(out, 2 * cnt, ncclDouble, partner, comm, stream_), "ncclSend");
+            nccl_check(nccl().Recv(in, 2 * cnt, ncclDouble, partner, comm, stream_), "ncclRecv");
+            nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+            cuda_check(cudaEventRecord(received_[sl], stream_), "record(received)");
+            cuda_check(cudaStreamWaitEvent(copy_stream_, received_[sl], 0), "wait(received)");
+            k::unpack_half(copy_stream_, shard, in, first, cnt, b, int(send_bit));
+            cuda_check(cudaEventRecord(copied_[sl], copy_stream_), "record(unpacked)");
+            if (bytes_sent) *bytes_sent += cnt * sizeof(double2);
+        }
+        for (int sl = 0; sl < 2 && uint64_t(sl) < i; ++sl)
+            cuda_check(cudaStreamWaitEvent(stream_, copied_[sl], 0), "wait(unpacked, final)");
+        return;
+    }
     const uint64_t slot_amps = staging_amps >= 2 ? staging_amps / 2 : staging_amps;
     const int n_slots = staging_amps >= 2 ? 2 : 1;
     const uint64_t piece = std::min<uint64_t>(block, slot_amps);

@@ -50,7 +50,8 @@ private:
     uint64_t free_mask_;
     cudaStream_t stream_;
     cudaStream_t copy_stream_ = nullptr;  // staging -> shard copies, overlapped with the next NVLink transfer
-    cudaEvent_t received_[2] = {nullptr, nullptr}, copied_[2] = {nullptr, nullptr};
+    cudaEvent_t received_[2] = {nullptr, nullptr}, copied_[2] = {nullptr, nullptr}, packed_[2] = {nullptr, nullptr};
+    cudaEvent_t ready_ = nullptr;
     void* comm_ = nullptr;
     double* d_buf_ = nullptr;  // device staging for scalar collectives
     size_t d_buf_doubles_ = 0;

@@ -462,6 +462,40 @@ void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices,
     launched(c);
 }
 
+// pack / unpack one half of the shard (local bit `pos` == vbit) for a global<->local qubit exchange: element j of the
+// half is shard[insert_bit(j, pos, vbit)].  `first` is the first j of this piece, `count` its length.
+__global__ void __launch_bounds__(256) pack_half_kernel(const double2* __restrict__ shard, double2* __restrict__ packed,
+                                                        uint64_t first, uint64_t count, int pos, uint64_t vbit) {
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += step)
+        packed[j] = shard[insert_zero_bit(first + j, pos) | vbit];
+}
+
+__global__ void __launch_bounds__(256) unpack_half_kernel(double2* __restrict__ shard, const double2* __restrict__ packed,
+                                                          uint64_t first, uint64_t count, int pos, uint64_t vbit) {
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += step)
+        shard[insert_zero_bit(first + j, pos) | vbit] = packed[j];
+}
+
+void pack_half(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, int pos,
+               int value) {
+    uint64_t blocks = (count + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    pack_half_kernel<<<unsigned(blocks), 256, 0, stream>>>(shard, packed, first, count, pos, uint64_t(value ? 1 : 0) << pos);
+    PQB_CUDA_CHECK(cudaGetLastError());
+}
+
+void unpack_half(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count, int pos,
+                 int value) {
+    uint64_t blocks = (count + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    unpack_half_kernel<<<unsigned(blocks), 256, 0, stream>>>(shard, packed, first, count, pos, uint64_t(value ? 1 : 0) << pos);
+    PQB_CUDA_CHECK(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // bin sums for the measurement search
 // ------------------------------------------------------------------------------------------------------------------

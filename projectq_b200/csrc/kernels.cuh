@@ -45,6 +45,10 @@ void permute_gather(const Ctx& c, const double2* in, double2* out, uint64_t n_am
 // out[j] = psi[indices[j]] for a handful of indices
 void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices, uint64_t n, double2* d_out);
 
+// remap support: gather / scatter the half of the shard whose local bit `pos` equals `value` (piece [first, first+count))
+void pack_half(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, int pos, int value);
+void unpack_half(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count, int pos, int value);
+
 // Measurement search support (reference: the serial inverse-CDF scan, simulator.hpp:156-158): sums of |psi|^2 over
 // bins.  The subspace is fixed_val on the positions in ins_pos that are neither bin bits; bin b covers the amplitudes
 // whose bits at bin_pos spell b.  ins_pos = ascending union of the fixed positions and bin positions.

@@ -19,6 +19,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     n_local = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+    low = len(sys.argv) > 2 and sys.argv[2] == "low"  # evict the lowest local bits (scattered halves -> packed exchange)
     g = int(np.log2(world))
     n = n_local + g
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -43,7 +44,16 @@ def main():
         # a k-qubit gate on all global qubits at once -> one multi-bit remap
         tq = list(range(n - g, n))
         sim.apply_controlled_gate(rand_unitary(rng, len(tq)), tq, [])
+        if low:  # pending work on every local qubit except the lowest g: those become the eviction victims
+            for q in range(g, n - g):
+                sim.apply_controlled_gate(m, [q], [])
         sim.run()
+        if low:
+            sim.synchronize()
+            st = sim.stats()
+            if rank == 0:
+                print(json.dumps({"mode": "low", "remaps": st["remaps"], "GBs_per_direction": st["remap_bytes_sent"] / max(st["remap_ms"], 1e-9) / 1e6}))
+            continue
         tq = list(range(n - 2 * g, n - g))
         sim.apply_controlled_gate(rand_unitary(rng, len(tq)), tq, [])
         sim.run()
