@@ -264,6 +264,11 @@ def main():
     remap_ms = st["remap_ms"] / args.steps
     launch_ms = (ms_per_step - remap_ms) / max(n_pass, 1)
     achieved = 32.0 * local_amps / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic_k4_30q.json")
+    if world == 1 and n == 30 and dom_k == 4 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["traffic_bytes_per_launch"]  # dram read+write of one launch, ncu --set full capture
     line = {
         "metric": "brickwork amp-updates/s", "value": value, "unit": "amp-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -275,7 +280,7 @@ def main():
                    % (16.0 * local_amps / 2**30), "parallelism": "state sharded by the top %d qubits" % int(np.log2(world)),
                    "norm_after": norm, "p0": p0, "sec_per_layer": ms_per_step * 1e-3 / DEPTH},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "kernel": "apply_dense_kernel<k=%d>" % dom_k, "avg_launch_ms": launch_ms,
                      "algorithmic_bytes_per_launch": 32.0 * local_amps},
         "e2e": {"value": e2e_value, "unit": "amp-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,

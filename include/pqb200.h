@@ -180,6 +180,10 @@ PQB_API int pqb_host_rng_stream(uint32_t seed, size_t n, double* out);
  * (rank bit, local bit) pairs to exchange */
 PQB_API int pqb_host_plan_remap(uint8_t* loc, size_t n_logical, int n_local_bits, const uint32_t* need, size_t n_need,
                                 int32_t* out_pairs, size_t cap_pairs, size_t* out_n_pairs);
+/* exchange plan of a (multi-bit) remap for one rank (dist.h plan_exchange): pairs = (rank bit, local bit) x n_pairs;
+ * for each partner rank the pattern of exchanged local bits of the sub-block swapped with it */
+PQB_API int pqb_host_plan_exchange(int rank, const int32_t* pairs, size_t n_pairs, int32_t* out_peers, uint64_t* out_patterns,
+                                   size_t cap, size_t* out_n);
 /* a fresh 128-byte ncclUniqueId (rank 0 creates it, the launcher's plumbing broadcasts it to the other ranks) */
 PQB_API int pqb_nccl_unique_id(void* out128);
 /* library version string */

@@ -297,6 +297,25 @@ int pqb_host_plan_remap(uint8_t* loc, size_t n_logical, int n_local_bits, const 
     }
 }
 
+int pqb_host_plan_exchange(int rank, const int32_t* pairs, size_t n_pairs, int32_t* out_peers, uint64_t* out_patterns,
+                           size_t cap, size_t* out_n) {
+    try {
+        std::vector<std::pair<int, int>> swaps;
+        for (size_t i = 0; i < n_pairs; ++i) swaps.emplace_back(pairs[2 * i], pairs[2 * i + 1]);
+        auto peers = pqb::plan_exchange(rank, swaps);
+        if (peers.size() > cap) return PQB_ERR_MEMORY;
+        for (size_t i = 0; i < peers.size(); ++i) {
+            out_peers[i] = peers[i].peer;
+            out_patterns[i] = peers[i].pattern;
+        }
+        *out_n = peers.size();
+        return PQB_OK;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return PQB_ERR_RUNTIME;
+    }
+}
+
 int pqb_nccl_unique_id(void* out128) {
     try {
         pqb::Dist::get_unique_id(out128);

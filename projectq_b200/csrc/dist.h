@@ -21,6 +21,16 @@ namespace pqb {
 std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_local_bits, const std::vector<uint32_t>& need,
                                             const std::vector<uint32_t>* victims = nullptr);
 
+// Who exchanges what in a (multi-bit) remap.  Exchanging rank bits r_i with local bits b_i sends, from every rank, the
+// sub-block whose local bits (b_i) spell beta to the rank whose bits (r_i) spell beta, and the sub-block that arrives from
+// that rank lands at the same addresses — so the remap is a set of pairwise in-place sub-block exchanges, one per peer
+// (an all-to-all inside the group of 2^g ranks that differ only in the exchanged rank bits).
+struct ExchangePeer {
+    int peer;          // partner rank
+    uint64_t pattern;  // values of the exchanged local bits (in place) of the sub-block swapped with that partner
+};
+std::vector<ExchangePeer> plan_exchange(int rank, const std::vector<std::pair<int, int>>& swaps);
+
 class Dist {
 public:
     Dist(int rank, int world, const void* nccl_unique_id, cudaStream_t stream);
@@ -37,6 +47,10 @@ public:
     // exchange rank bit r with local bit b (n_local_bits = log2 n_amps); staging: >= staging_amps device amplitudes
     void swap_bits(int r, int b, double2* shard, int n_local_bits, double2* staging, uint64_t staging_amps,
                    uint64_t* bytes_sent);
+
+    // exchange several (rank bit, local bit) pairs at once: every rank sends 1 - 2^-g of its shard instead of g/2
+    void swap_bits_multi(const std::vector<std::pair<int, int>>& swaps, double2* shard, int n_local_bits, double2* staging,
+                         uint64_t staging_amps, uint64_t* bytes_sent);
 
     double allreduce_sum(double v);
     void allreduce_sum_vec(double* v, size_t n);  // host vector, in place

@@ -84,6 +84,8 @@ Engine::~Engine() {
     if (d_flush_) cudaFree(d_flush_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    if (remap_e0_) cudaEventDestroy(remap_e0_);
+    if (remap_e1_) cudaEventDestroy(remap_e1_);
     for (auto& b : buf_) b.release();
     if (stream_) cudaStreamDestroy(stream_);
 }
@@ -373,26 +375,34 @@ void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uin
     // staging: a bounded slice of the second scratch buffer (the state itself may fill most of HBM)
     const uint64_t want = std::min<uint64_t>(local_amps() >> 1, uint64_t(1) << 26);  // <= 1 GiB
     ensure_scratch(*scratch2_, std::max<uint64_t>(want, 1) * sizeof(double2));
-    cudaEvent_t e0, e1;
-    PQB_CHECK(cudaEventCreate(&e0));
-    PQB_CHECK(cudaEventCreate(&e1));
+    // ev0_/ev1_ belong to the user-facing stopwatch (timer_start/timer_stop), so remaps time themselves with their own pair
+    if (!remap_e0_) {
+        PQB_CHECK(cudaEventCreate(&remap_e0_));
+        PQB_CHECK(cudaEventCreate(&remap_e1_));
+    }
+    cudaEvent_t e0 = remap_e0_, e1 = remap_e1_;
     PQB_CHECK(cudaEventRecord(e0, stream_));
-    for (auto& sw : swaps) {
-        try {
-            dist_->swap_bits(sw.first, sw.second, psi(), L_, scratch2_->amps(), std::max<uint64_t>(want, 1),
-                             &stats_.remap_bytes_sent);
-        } catch (const std::runtime_error& e) {
-            throw CudaErr(e.what());
+    try {
+        // one grouped exchange for all bits when the staging slice can be cut into 4 slots per peer; else bit by bit
+        const uint64_t peers = (uint64_t(1) << swaps.size()) - 1;
+        if (swaps.size() >= 2 && swaps.size() <= 8 && want >= 4 * peers) {
+            dist_->swap_bits_multi(swaps, psi(), L_, scratch2_->amps(), want, &stats_.remap_bytes_sent);
+            ++stats_.remaps;
+        } else {
+            for (auto& sw : swaps) {
+                dist_->swap_bits(sw.first, sw.second, psi(), L_, scratch2_->amps(), std::max<uint64_t>(want, 1),
+                                 &stats_.remap_bytes_sent);
+                ++stats_.remaps;
+            }
         }
-        ++stats_.remaps;
+    } catch (const std::runtime_error& e) {
+        throw CudaErr(e.what());
     }
     PQB_CHECK(cudaEventRecord(e1, stream_));
     PQB_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     stats_.remap_ms += ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
 }
 
 void Engine::run() {
@@ -473,6 +483,33 @@ void Engine::run_sharded() {
             });
             std::vector<uint32_t> victims;
             for (auto& u : use) victims.push_back(u.second);
+            // While we are paying for an exchange, bring in the other rank-bit qubits too if they are needed sooner than
+            // the local qubits they would replace: one grouped all-to-all moves 1 - 2^-g of a shard, g separate remaps
+            // move g/2.
+            std::vector<std::pair<size_t, uint32_t>> incoming;
+            for (auto& kv : map_)
+                if (!is_local(kv.second) && std::find(need.begin(), need.end(), kv.second) == need.end())
+                    incoming.emplace_back(fuser_.next_use(kv.first), kv.second);
+            std::sort(incoming.begin(), incoming.end());
+            size_t n_global_needed = 0;
+            for (auto lp : need)
+                if (!is_local(lp)) ++n_global_needed;
+            for (auto& in : incoming) {
+                if (in.first == size_t(-1)) break;                      // never used again
+                size_t vi = n_global_needed;                             // the victim this qubit would displace
+                size_t seen = 0;
+                const std::pair<size_t, uint32_t>* victim = nullptr;
+                for (auto& u : use) {
+                    if (std::find(need.begin(), need.end(), u.second) != need.end()) continue;
+                    if (seen++ == vi) {
+                        victim = &u;
+                        break;
+                    }
+                }
+                if (!victim || victim->first <= in.first) break;        // the local qubit is needed sooner: keep it
+                need.push_back(in.second);
+                ++n_global_needed;
+            }
             make_local(need, &victims);
         }
     } catch (...) {

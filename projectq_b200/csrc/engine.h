@@ -116,6 +116,7 @@ private:
     int sm_count_ = 148;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    cudaEvent_t remap_e0_ = nullptr, remap_e1_ = nullptr;
     GrowBuffer buf_[3];
     GrowBuffer* state_ = &buf_[0];
     GrowBuffer* scratch1_ = &buf_[1];

@@ -462,38 +462,68 @@ void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices,
     launched(c);
 }
 
-// pack / unpack one half of the shard (local bit `pos` == vbit) for a global<->local qubit exchange: element j of the
-// half is shard[insert_bit(j, pos, vbit)].  `first` is the first j of this piece, `count` its length.
-__global__ void __launch_bounds__(256) pack_half_kernel(const double2* __restrict__ shard, double2* __restrict__ packed,
-                                                        uint64_t first, uint64_t count, int pos, uint64_t vbit) {
+// pack / unpack one sub-block of the shard for a global<->local qubit exchange: the sub-block is the set of amplitudes
+// whose local bits at `pos` (ascending) spell `pattern`; element j of it is shard[insert_zero_bits(j, pos) | pattern].
+// `first` is the first j of this piece, `count` its length.
+struct SubBlockArgs {
+    uint64_t first, count, pattern;
+    int n_pos;
+    uint8_t pos[8];
+};
+
+__global__ void __launch_bounds__(256) pack_sub_kernel(const double2* __restrict__ shard, double2* __restrict__ packed,
+                                                       const __grid_constant__ SubBlockArgs a) {
     const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
-    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += step)
-        packed[j] = shard[insert_zero_bit(first + j, pos) | vbit];
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < a.count; j += step)
+        packed[j] = shard[insert_zero_bits(a.first + j, a.pos, a.n_pos) | a.pattern];
 }
 
-__global__ void __launch_bounds__(256) unpack_half_kernel(double2* __restrict__ shard, const double2* __restrict__ packed,
-                                                          uint64_t first, uint64_t count, int pos, uint64_t vbit) {
+__global__ void __launch_bounds__(256) unpack_sub_kernel(double2* __restrict__ shard, const double2* __restrict__ packed,
+                                                         const __grid_constant__ SubBlockArgs a) {
     const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
-    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += step)
-        shard[insert_zero_bit(first + j, pos) | vbit] = packed[j];
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < a.count; j += step)
+        shard[insert_zero_bits(a.first + j, a.pos, a.n_pos) | a.pattern] = packed[j];
+}
+
+static SubBlockArgs sub_args(uint64_t first, uint64_t count, const uint8_t* pos, int n_pos, uint64_t pattern) {
+    if (n_pos > 8) throw std::invalid_argument("pack_sub: more than 8 exchanged bits");
+    SubBlockArgs a{};
+    a.first = first;
+    a.count = count;
+    a.pattern = pattern;
+    a.n_pos = n_pos;
+    for (int i = 0; i < n_pos; ++i) a.pos[i] = pos[i];
+    return a;
+}
+
+static unsigned sub_grid(uint64_t count) {
+    uint64_t blocks = (count + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    return unsigned(blocks < 1 ? 1 : blocks);
+}
+
+void pack_sub(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count,
+              const uint8_t* pos, int n_pos, uint64_t pattern) {
+    pack_sub_kernel<<<sub_grid(count), 256, 0, stream>>>(shard, packed, sub_args(first, count, pos, n_pos, pattern));
+    PQB_CUDA_CHECK(cudaGetLastError());
+}
+
+void unpack_sub(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count,
+                const uint8_t* pos, int n_pos, uint64_t pattern) {
+    unpack_sub_kernel<<<sub_grid(count), 256, 0, stream>>>(shard, packed, sub_args(first, count, pos, n_pos, pattern));
+    PQB_CUDA_CHECK(cudaGetLastError());
 }
 
 void pack_half(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, int pos,
                int value) {
-    uint64_t blocks = (count + 256 * 4 - 1) / (256 * 4);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    pack_half_kernel<<<unsigned(blocks), 256, 0, stream>>>(shard, packed, first, count, pos, uint64_t(value ? 1 : 0) << pos);
-    PQB_CUDA_CHECK(cudaGetLastError());
+    const uint8_t p = uint8_t(pos);
+    pack_sub(stream, shard, packed, first, count, &p, 1, uint64_t(value ? 1 : 0) << pos);
 }
 
 void unpack_half(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count, int pos,
                  int value) {
-    uint64_t blocks = (count + 256 * 4 - 1) / (256 * 4);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    unpack_half_kernel<<<unsigned(blocks), 256, 0, stream>>>(shard, packed, first, count, pos, uint64_t(value ? 1 : 0) << pos);
-    PQB_CUDA_CHECK(cudaGetLastError());
+    const uint8_t p = uint8_t(pos);
+    unpack_sub(stream, shard, packed, first, count, &p, 1, uint64_t(value ? 1 : 0) << pos);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

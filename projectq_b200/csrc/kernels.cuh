@@ -48,6 +48,11 @@ void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices,
 // remap support: gather / scatter the half of the shard whose local bit `pos` equals `value` (piece [first, first+count))
 void pack_half(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, int pos, int value);
 void unpack_half(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count, int pos, int value);
+// same for the sub-block whose local bits at pos[0..n_pos) (ascending) spell `pattern` (multi-bit exchange)
+void pack_sub(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, const uint8_t* pos,
+              int n_pos, uint64_t pattern);
+void unpack_sub(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count,
+                const uint8_t* pos, int n_pos, uint64_t pattern);
 
 // Measurement search support (reference: the serial inverse-CDF scan, simulator.hpp:156-158): sums of |psi|^2 over
 // bins.  The subspace is fixed_val on the positions in ins_pos that are neither bin bits; bin b covers the amplitudes

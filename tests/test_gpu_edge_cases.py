@@ -1,0 +1,241 @@
+"""Edge cases of the native seam on the GPU, against the compiled reference / the NumPy oracle: empty and tiny states, empty
+argument lists, RNG consumption, non-classical probes, precondition-violating math gates, queue limits."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.statevec_oracle import OracleSimulator
+from tests.conftest import load_ref_cppsim
+from tests.helpers import rand_state, rand_unitary
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def Backend():
+    from projectq_b200.backend import SimulatorBackend
+
+    return SimulatorBackend
+
+
+def checker(seed=1):
+    mod = load_ref_cppsim()
+    return mod.Simulator(seed) if mod is not None else OracleSimulator(seed)
+
+
+def is_ref(chk):
+    return not isinstance(chk, OracleSimulator)
+
+
+def marg(chk, m):
+    return m.tolist() if is_ref(chk) else m
+
+
+def warg(chk, w):
+    return list(w) if is_ref(chk) else w
+
+
+def same(gpu, chk, tol=TOL):
+    m1, v1 = gpu.cheat()
+    m2, v2 = chk.cheat()
+    assert dict(m1) == dict(m2)
+    assert np.max(np.abs(np.asarray(v1) - np.asarray(v2))) < tol
+
+
+def test_zero_qubit_state(Backend):
+    s = Backend(1)
+    mapping, vec = s.cheat()
+    assert dict(mapping) == {} and list(vec) == [1 + 0j]
+    assert s.measure_qubits([]) == []
+    assert s.get_probability([], []) == 1.0
+    assert s.get_amplitude([], []) == 1 + 0j
+    assert s.get_expectation_value([([], 2.5)], []) == 2.5
+    s.run()
+    s.collapse_wavefunction([], [])
+    s.set_wavefunction(np.array([1j]), [])
+    assert s.get_amplitude([], []) == 1j
+
+
+def test_single_qubit_everything(Backend):
+    gpu, chk = Backend(9), checker(9)
+    for s in (gpu, chk):
+        s.allocate_qubit(42)
+    h = np.array([[1, 1], [1, -1]], dtype=np.complex128) / math.sqrt(2)
+    gpu.apply_controlled_gate(h, [42], [])
+    chk.apply_controlled_gate(marg(chk, h), [42], [])
+    same(gpu, chk)
+    assert abs(gpu.get_probability([True], [42]) - 0.5) < TOL
+    assert gpu.is_classical(42, 1e-12) is False
+    assert gpu.get_classical_value(42, 1e-12) == chk.get_classical_value(42, 1e-12)
+    assert list(gpu.measure_qubits([42])) == list(chk.measure_qubits([42]))
+    same(gpu, chk)
+    gpu.deallocate_qubit(42)
+    chk.deallocate_qubit(42)
+    same(gpu, chk)
+
+
+def test_empty_measurement_consumes_one_draw(Backend):
+    """the reference draws from its RNG once per measure_qubits call, even for an empty id list (simulator.hpp:153)"""
+    gpu, chk = Backend(5), checker(5)
+    h = np.array([[1, 1], [1, -1]], dtype=np.complex128) / math.sqrt(2)
+    for q in range(6):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+        gpu.apply_controlled_gate(h, [q], [])
+        chk.apply_controlled_gate(marg(chk, h), [q], [])
+    assert list(gpu.measure_qubits([])) == list(chk.measure_qubits([])) == []
+    same(gpu, chk)
+    for q in range(6):
+        assert list(gpu.measure_qubits([q])) == list(chk.measure_qubits([q]))
+    # duplicate ids in one call
+    for q in range(6):
+        gpu.apply_controlled_gate(h, [q], [])
+        chk.apply_controlled_gate(marg(chk, h), [q], [])
+    assert list(gpu.measure_qubits([2, 2, 4])) == list(chk.measure_qubits([2, 2, 4]))
+    same(gpu, chk)
+
+
+def test_measurement_of_unnormalised_state_takes_last_index(Backend):
+    """if the running sum never reaches the draw the reference ends on the last index (simulator.hpp:156-160);
+    seed 1 draws 0.997... first"""
+    gpu, chk = Backend(1), checker(1)
+    n = 5
+    for q in range(n):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    wf = np.full(1 << n, 0.1 + 0j)  # total probability 0.32
+    gpu.set_wavefunction(wf, list(range(n)))
+    chk.set_wavefunction(warg(chk, wf), list(range(n)))
+    a, b = list(gpu.measure_qubits([0, 3, 4])), list(chk.measure_qubits([0, 3, 4]))
+    assert a == b == [True, True, True]
+    same(gpu, chk)
+
+
+def test_get_classical_value_on_superpositions(Backend):
+    rng = np.random.default_rng(8)
+    n = 7
+    for trial in range(6):
+        gpu, chk = Backend(1), checker(1)
+        for q in range(n):
+            gpu.allocate_qubit(q)
+            chk.allocate_qubit(q)
+        wf = rand_state(rng, n)
+        wf[rng.random(1 << n) < 0.6] = 0  # many exact zeros so that the scan order matters
+        wf /= np.linalg.norm(wf)
+        order = [int(x) for x in rng.permutation(n)]
+        gpu.set_wavefunction(wf, order)
+        chk.set_wavefunction(warg(chk, wf), order)
+        gpu.deallocate_qubit  # noqa: B018  (no call: just keep both objects alive)
+        for q in range(n):
+            assert gpu.is_classical(q, 1e-12) == chk.is_classical(q, 1e-12)
+            assert gpu.get_classical_value(q, 1e-12) == chk.get_classical_value(q, 1e-12), (trial, q)
+
+
+def test_operator_corner_cases(Backend):
+    rng = np.random.default_rng(2)
+    n = 6
+    gpu, chk = Backend(1), checker(1)
+    for q in range(n):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    wf = rand_state(rng, n)
+    gpu.set_wavefunction(wf, list(range(n)))
+    chk.set_wavefunction(warg(chk, wf), list(range(n)))
+    ids = list(range(n))
+    assert gpu.get_expectation_value([], ids) == 0.0
+    # identity-only Hamiltonian: a pure phase (simulator.hpp:396-400,431-436)
+    gpu.emulate_time_evolution([([], 0.7)], 1.3, ids, [])
+    chk.emulate_time_evolution([([], 0.7)], 1.3, ids, [])
+    same(gpu, chk)
+    gpu.emulate_time_evolution([], 0.5, ids, [2])
+    chk.emulate_time_evolution([], 0.5, ids, [2])
+    same(gpu, chk)
+    # negative time, control, a 5-body term
+    terms = [([(0, "X"), (1, "Y"), (2, "Z"), (3, "X"), (4, "Y")], 0.8), ([(5, "Z")], -0.3), ([], 0.1)]
+    gpu.emulate_time_evolution(terms, -0.6, ids, [])
+    chk.emulate_time_evolution(terms, -0.6, ids, [])
+    same(gpu, chk)
+    # empty operator annihilates the state
+    gpu.apply_qubit_operator([], ids)
+    chk.apply_qubit_operator([], ids)
+    same(gpu, chk)
+    assert np.all(np.asarray(gpu.cheat()[1]) == 0)
+
+
+def test_math_gate_precondition_violations_accumulate(Backend):
+    """(x + a) % N with register values >= N: several sources land on one target and are summed (simulator.hpp:261)"""
+    n = 6
+    gpu, chk = Backend(1), checker(1)
+    for q in range(n):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    wf = (np.arange(1, (1 << n) + 1) + 0j) / 100.0
+    gpu.set_wavefunction(wf, list(range(n)))
+    chk.set_wavefunction(warg(chk, wf), list(range(n)))
+    for s in (gpu, chk):
+        s.emulate_math_addConstantModN(3, 5, [[0, 1, 2, 3]], [5])
+    same(gpu, chk, tol=1e-14)
+    for s in (gpu, chk):
+        s.emulate_math_multiplyByConstantModN(2, 6, [[0, 1, 2]], [])
+    same(gpu, chk, tol=1e-14)
+    # empty register list and an empty register are no-ops
+    for s in (gpu, chk):
+        s.emulate_math_addConstant(7, [], [])
+        s.emulate_math_addConstant(7, [[]], [0])
+    same(gpu, chk, tol=1e-14)
+
+
+def test_queue_limit_and_many_controls(Backend):
+    rng = np.random.default_rng(12)
+    n = 12
+    gpu, chk = Backend(1), OracleSimulator(1)
+    for q in range(n):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    h = np.array([[1, 1], [1, -1]], dtype=np.complex128) / math.sqrt(2)
+    for q in range(n):
+        gpu.apply_controlled_gate(h, [q], [])
+        chk.apply_controlled_gate(h, [q], [])
+    # more gates than the engine buffers before draining on its own (4096)
+    gates = []
+    for g in range(4500):
+        q = int(rng.integers(0, n))
+        th = float(rng.uniform(0, 6.28))
+        m = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]], dtype=np.complex128)
+        gates.append((m, q))
+    for m, q in gates:
+        gpu.apply_controlled_gate(m, [q], [])
+        chk.apply_controlled_gate(m, [q], [])
+    # a 10-fold controlled gate and a gate whose controls are all the other qubits
+    m = rand_unitary(rng, 1)
+    gpu.apply_controlled_gate(m, [11], list(range(10)))
+    chk.apply_controlled_gate(m, [11], list(range(10)))
+    m2 = rand_unitary(rng, 2)
+    gpu.apply_controlled_gate(m2, [3, 7], [q for q in range(n) if q not in (3, 7)])
+    chk.apply_controlled_gate(m2, [3, 7], [q for q in range(n) if q not in (3, 7)])
+    same(gpu, chk, tol=1e-11)  # 4500 sequential rotations: rounding accumulates differently in fused form
+
+
+def test_id_reuse_and_noncontiguous_ids(Backend):
+    rng = np.random.default_rng(4)
+    gpu, chk = Backend(2), checker(2)
+    ids = [7, 1000000, 3, 4000000000]
+    for q in ids:
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    for g in range(20):
+        qs = [int(x) for x in rng.permutation(ids)[:3]]
+        m = rand_unitary(rng, 2)
+        gpu.apply_controlled_gate(m, qs[:2], qs[2:])
+        chk.apply_controlled_gate(marg(chk, m), qs[:2], qs[2:])
+    assert list(gpu.measure_qubits([3])) == list(chk.measure_qubits([3]))
+    gpu.deallocate_qubit(3)
+    chk.deallocate_qubit(3)
+    gpu.allocate_qubit(3)
+    chk.allocate_qubit(3)
+    m = rand_unitary(rng, 2)
+    gpu.apply_controlled_gate(m, [3, 7], [])
+    chk.apply_controlled_gate(marg(chk, m), [3, 7], [])
+    same(gpu, chk)

@@ -165,3 +165,50 @@ def test_remap_planner(lib):
     st = lib.pqb_host_plan_remap(loc2, ctypes.c_size_t(3), ctypes.c_int(2), need2, ctypes.c_size_t(3), pairs,
                                  ctypes.c_size_t(4), ctypes.byref(n_pairs))
     assert st == 1
+
+
+def test_exchange_plan_is_the_bit_swap_permutation(lib):
+    """simulate the multi-bit remap on NumPy shards: following plan_exchange on every rank must realise exactly the
+    permutation 'exchange rank bit r_i with local bit b_i' of the global index"""
+    g_total, L = 3, 6
+    world = 1 << g_total
+    for swaps in ([(0, 5)], [(2, 0)], [(0, 5), (2, 1)], [(1, 0), (0, 3), (2, 4)]):
+        shards = [np.arange(1 << L, dtype=np.int64) + (r << L) for r in range(world)]  # value = old global index
+        new = [s.copy() for s in shards]
+        pos = sorted(b for _, b in swaps)
+
+        def members(pattern):
+            idx = []
+            for j in range(1 << (L - len(pos))):
+                x = j
+                for p in pos:
+                    x = ((x >> p) << (p + 1)) | (x & ((1 << p) - 1))
+                idx.append(x | pattern)
+            return np.array(idx)
+
+        pairs = (ctypes.c_int32 * (2 * len(swaps)))(*[v for rb in swaps for v in rb])
+        plans = []
+        for rank in range(world):
+            peers = (ctypes.c_int32 * 8)()
+            pats = (ctypes.c_uint64 * 8)()
+            n = ctypes.c_size_t()
+            assert lib.pqb_host_plan_exchange(rank, pairs, ctypes.c_size_t(len(swaps)), peers, pats, ctypes.c_size_t(8),
+                                              ctypes.byref(n)) == 0
+            assert n.value == (1 << len(swaps)) - 1
+            plans.append({int(peers[i]): int(pats[i]) for i in range(n.value)})
+        for rank in range(world):
+            for peer, pattern in plans[rank].items():
+                # this rank packs its sub-block `pattern` for the partner; the partner unpacks it into the sub-block it
+                # exchanges with this rank (each rank sends from and receives into the same addresses)
+                new[peer][members(plans[peer][rank])] = shards[rank][members(pattern)]
+        for rank in range(world):
+            for local in range(1 << L):
+                old = int(new[rank][local])
+                orank, olocal = old >> L, old & ((1 << L) - 1)
+                # exchanging the bit pairs of (orank, olocal) must give (rank, local)
+                er, el = orank, olocal
+                for r, b in swaps:
+                    rb, lb = (er >> r) & 1, (el >> b) & 1
+                    er = (er & ~(1 << r)) | (lb << r)
+                    el = (el & ~(1 << b)) | (rb << b)
+                assert (er, el) == (rank, local)
