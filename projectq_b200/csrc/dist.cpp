@@ -100,7 +100,11 @@ std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_loc
 std::vector<ExchangePeer> plan_exchange(int rank, const std::vector<std::pair<int, int>>& swaps) {
     std::vector<ExchangePeer> out;
     const int g = int(swaps.size());
-    for (uint64_t beta = 0; beta < (uint64_t(1) << g); ++beta) {
+    uint64_t mine = 0;  // this rank's value of the exchanged rank bits
+    for (int i = 0; i < g; ++i) mine |= uint64_t((rank >> swaps[i].first) & 1) << i;
+    // round k pairs beta with beta ^ k: every round is a perfect matching, so the pairwise rounds never wait on a third rank
+    for (uint64_t k = 1; k < (uint64_t(1) << g); ++k) {
+        const uint64_t beta = mine ^ k;
         int peer = rank;
         uint64_t pattern = 0;
         for (int i = 0; i < g; ++i) {
@@ -108,7 +112,7 @@ std::vector<ExchangePeer> plan_exchange(int rank, const std::vector<std::pair<in
             peer = (peer & ~(1 << swaps[i].first)) | (bit << swaps[i].first);
             pattern |= uint64_t(bit) << swaps[i].second;
         }
-        if (peer != rank) out.push_back({peer, pattern});
+        out.push_back({peer, pattern});
     }
     return out;
 }
@@ -306,35 +310,35 @@ void Dist::swap_bits_multi(const std::vector<std::pair<int, int>>& swaps, double
     for (int i = 0; i < g; ++i) pos[i] = uint8_t(swaps[i].second);
     std::sort(pos, pos + g);
     const uint64_t sub_amps = uint64_t(1) << (n_local_bits - g);  // amplitudes per sub-block
-    const uint64_t slot = staging_amps / (4 * P);                  // per peer, per direction, per buffer
+    const uint64_t slot = staging_amps / 4;                        // out/in x double buffer
     if (slot == 0) throw std::runtime_error("swap_bits_multi: staging area too small");
     ncclComm_t comm = static_cast<ncclComm_t>(comm_);
     cuda_check(cudaEventRecord(ready_, stream_), "record(ready)");
-    auto out_slot = [&](int sl, uint64_t p) { return staging + (uint64_t(sl) * P + p) * slot; };
-    auto in_slot = [&](int sl, uint64_t p) { return staging + ((2 + uint64_t(sl)) * P + p) * slot; };
+    // Pairwise rounds (peer after peer) rather than one NCCL group with all peers: measured on 4 GPUs, a grouped
+    // exchange with 3 peers at once moves 245 GB/s per direction, pair exchanges 440-570 GB/s.  The pieces of all rounds
+    // form one pipeline: the side stream packs piece i+1 and unpacks piece i-1 while piece i is on the wire.
     uint64_t i = 0;
-    for (uint64_t first = 0; first < sub_amps; first += slot, ++i) {
-        const uint64_t cnt = std::min(slot, sub_amps - first);
-        const int sl = int(i % 2);
-        // side stream: gather piece i of every outgoing sub-block (after the sends of piece i-2 have drained the slots)
-        cuda_check(cudaStreamWaitEvent(copy_stream_, i >= 2 ? received_[sl] : ready_, 0), "wait(slot free)");
-        for (uint64_t p = 0; p < P; ++p) k::pack_sub(copy_stream_, shard, out_slot(sl, p), first, cnt, pos, g, peers[p].pattern);
-        cuda_check(cudaEventRecord(packed_[sl], copy_stream_), "record(packed)");
-        // main stream: one grouped exchange with all peers = all-to-all over NVSwitch
-        cuda_check(cudaStreamWaitEvent(stream_, packed_[sl], 0), "wait(packed)");
-        if (i >= 2) cuda_check(cudaStreamWaitEvent(stream_, copied_[sl], 0), "wait(unpacked)");
-        nccl_check(nccl().GroupStart(), "ncclGroupStart");
-        for (uint64_t p = 0; p < P; ++p) {
-            nccl_check(nccl().Send(out_slot(sl, p), 2 * cnt, ncclDouble, peers[p].peer, comm, stream_), "ncclSend");
-            nccl_check(nccl().Recv(in_slot(sl, p), 2 * cnt, ncclDouble, peers[p].peer, comm, stream_), "ncclRecv");
+    for (uint64_t p = 0; p < P; ++p) {
+        for (uint64_t first = 0; first < sub_amps; first += slot, ++i) {
+            const uint64_t cnt = std::min(slot, sub_amps - first);
+            const int sl = int(i % 2);
+            double2* out = staging + uint64_t(sl) * slot;
+            double2* in = staging + uint64_t(2 + sl) * slot;
+            cuda_check(cudaStreamWaitEvent(copy_stream_, i >= 2 ? received_[sl] : ready_, 0), "wait(slot free)");
+            k::pack_sub(copy_stream_, shard, out, first, cnt, pos, g, peers[p].pattern);
+            cuda_check(cudaEventRecord(packed_[sl], copy_stream_), "record(packed)");
+            cuda_check(cudaStreamWaitEvent(stream_, packed_[sl], 0), "wait(packed)");
+            if (i >= 2) cuda_check(cudaStreamWaitEvent(stream_, copied_[sl], 0), "wait(unpacked)");
+            nccl_check(nccl().GroupStart(), "ncclGroupStart");
+            nccl_check(nccl().Send(out, 2 * cnt, ncclDouble, peers[p].peer, comm, stream_), "ncclSend");
+            nccl_check(nccl().Recv(in, 2 * cnt, ncclDouble, peers[p].peer, comm, stream_), "ncclRecv");
+            nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+            cuda_check(cudaEventRecord(received_[sl], stream_), "record(received)");
+            cuda_check(cudaStreamWaitEvent(copy_stream_, received_[sl], 0), "wait(received)");
+            k::unpack_sub(copy_stream_, shard, in, first, cnt, pos, g, peers[p].pattern);
+            cuda_check(cudaEventRecord(copied_[sl], copy_stream_), "record(unpacked)");
+            if (bytes_sent) *bytes_sent += cnt * sizeof(double2);
         }
-        nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
-        cuda_check(cudaEventRecord(received_[sl], stream_), "record(received)");
-        // side stream: scatter the arrivals into place
-        cuda_check(cudaStreamWaitEvent(copy_stream_, received_[sl], 0), "wait(received)");
-        for (uint64_t p = 0; p < P; ++p) k::unpack_sub(copy_stream_, shard, in_slot(sl, p), first, cnt, pos, g, peers[p].pattern);
-        cuda_check(cudaEventRecord(copied_[sl], copy_stream_), "record(unpacked)");
-        if (bytes_sent) *bytes_sent += P * cnt * sizeof(double2);
     }
     for (int sl = 0; sl < 2 && uint64_t(sl) < i; ++sl)
         cuda_check(cudaStreamWaitEvent(stream_, copied_[sl], 0), "wait(unpacked, final)");

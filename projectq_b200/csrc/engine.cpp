@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -383,9 +384,15 @@ void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uin
     cudaEvent_t e0 = remap_e0_, e1 = remap_e1_;
     PQB_CHECK(cudaEventRecord(e0, stream_));
     try {
-        // one grouped exchange for all bits when the staging slice can be cut into 4 slots per peer; else bit by bit
-        const uint64_t peers = (uint64_t(1) << swaps.size()) - 1;
-        if (swaps.size() >= 2 && swaps.size() <= 8 && want >= 4 * peers) {
+        // Several bits at once can go as one all-to-all (pairwise rounds over sub-blocks, 1 - 2^-g of the shard instead of
+        // g/2).  Measured on 4 GPUs it is slower so far (213-245 GB/s per direction against 440-570 for single-bit
+        // exchanges, so 60 ms against 39 ms for two bits of a 16 GiB shard): opt-in (PQB_REMAP_MULTI=1) until that is
+        // understood; the default exchanges bit by bit.
+        static const bool multi = [] {
+            const char* e = getenv("PQB_REMAP_MULTI");
+            return e && e[0] == '1';
+        }();
+        if (multi && swaps.size() >= 2 && swaps.size() <= 8 && want >= 4) {
             dist_->swap_bits_multi(swaps, psi(), L_, scratch2_->amps(), want, &stats_.remap_bytes_sent);
             ++stats_.remaps;
         } else {
