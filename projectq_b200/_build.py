@@ -46,7 +46,7 @@ def build_lib(force=False):
                   "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(ROOT, "include"),
                   "-x", "cu" if s.endswith(".cu") else "c++", "-c", s, "-o", o])
         objs.append(o)
-    _run([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "shared", "-ldl"])
+    _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-cudart", "shared", "-ldl"])
     return LIB
 
 

@@ -15,7 +15,7 @@ struct pqb_sim {
 };
 
 namespace {
-std::string g_create_error;
+thread_local std::string g_create_error;  // message of the last failing call that has no handle to hang it on
 
 template <class F>
 int guarded(pqb_sim* s, F&& f) {

@@ -85,8 +85,6 @@ public:
     double measure_fp64_peak();
     double measure_copy_bandwidth(size_t bytes);
 
-    std::string last_error;
-
 private:
     k::Ctx ctx() { return k::Ctx{stream_, &stats_.kernel_launches}; }
     uint64_t local_amps() const { return uint64_t(1) << L_; }
@@ -102,7 +100,6 @@ private:
     double read_scalar(const double* d_ptr);
     double allreduce_sum(double v);
     void ensure_scratch(GrowBuffer& b, size_t bytes);
-    void swap_state(GrowBuffer*& other);
     std::vector<k::PauliTerm> build_terms(const TermsView& t, const uint32_t* ids, size_t n_ids, bool skip_identity,
                                           double* identity_sum_re, double* identity_sum_im);
     void make_local(const std::vector<uint32_t>& logical_positions, const std::vector<uint32_t>* victims = nullptr);

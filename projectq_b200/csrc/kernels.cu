@@ -216,7 +216,7 @@ static void launch_dense_mode(const Ctx& c, double2* psi, const DenseArgs<K>& ar
 template <int K, int U0, int T0>
 static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
                          const double* m_host) {
-    static DenseArgs<K> args;  // staging for the parameter block (copied by the launch)
+    DenseArgs<K> args;  // parameter block (copied by the launch); on the stack so concurrent engines do not share it
     const bool bit0_target = tpos[0] == 0;
     if (bit0_target) {
         fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host);
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) apply_diag_kernel(double2* __restrict__ p
 void apply_diagonal(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl,
                     const uint8_t* cpos, const double* d_host) {
     if (k > 5) throw std::invalid_argument("apply_diagonal: k > 5");
-    static DiagArgs a;
+    DiagArgs a{};
     for (int i = 0; i < (1 << k); ++i) a.d[i] = make_double2(d_host[2 * i], d_host[2 * i + 1]);
     a.k = k;
     a.n_ctrl = n_ctrl;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) classical_probe_kernel(const double2* __r
 
 void classical_probe(const Ctx& c, const double2* psi, uint64_t n_amps, int pos_phys, int pos_log, double tol,
                      const uint8_t* phys2log, int n_total_bits, uint64_t rank_bits, unsigned long long* d_out2) {
-    static ProbeArgs a;
+    ProbeArgs a{};
     a.n_amps = n_amps;
     a.rank_bits = rank_bits;
     a.tol = tol;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(256) permute_gather_kernel(const double2* __re
 }
 
 void permute_gather(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, int n_bits, const uint8_t* perm) {
-    static PermArgs a;
+    PermArgs a{};
     a.n_amps = n_amps;
     a.n_bits = n_bits;
     for (int b = 0; b < n_bits; ++b) a.perm[b] = perm[b];
@@ -583,7 +583,7 @@ __global__ void bin_sums_thread_kernel(const double2* __restrict__ psi, const __
 void bin_sums(const Ctx& c, const double2* psi, int n_bits, int n_ins, const uint8_t* ins_pos, uint64_t fixed_val, int m,
               const uint8_t* bin_pos, double* d_partials, double* d_bins) {
     if (m > 12 || n_ins > 64 || n_ins > n_bits) throw std::invalid_argument("bin_sums: bad arguments");
-    static BinArgs a;
+    BinArgs a{};
     a.fixed_val = fixed_val;
     a.n_ins = n_ins;
     a.m = m;
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(256) pauli_expectation_kernel(const double2* _
 void pauli_expectation_group(const Ctx& c, const double2* psi, int n_bits, uint64_t xmask, const PauliTerm* terms,
                              int n_terms, double* d_partials, double* d_acc) {
     if (n_terms > 64) throw std::invalid_argument("pauli_expectation_group: more than 64 terms per launch");
-    static ExpArgs a;
+    ExpArgs a{};
     for (int t = 0; t < n_terms; ++t) a.t[t] = terms[t];
     a.n_terms = n_terms;
     a.xmask = xmask;
