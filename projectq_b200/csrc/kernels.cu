@@ -180,6 +180,97 @@ __global__ void __launch_bounds__(THREADS, MINB) apply_dense_kernel(double2* __r
     }
 }
 
+// MODE 2 (separate kernel): the C lowest bits are all targets (C >= 2) and the next five bits are free.  A thread's members
+// with the low bits varying are one contiguous run of 2^C amplitudes and neighbouring lanes are 2^C amplitudes apart, so
+// per-lane accesses — even 256-bit ones — touch 32 different lines per request (measured 4.8-5.4 TB/s).  Here the warp
+// moves each run of 32 * 2^C amplitudes with perfectly coalesced 512-byte requests and transposes it through a padded
+// shared-memory tile (row = lane's group, 2^C + 1 slots wide: conflict-free on the per-lane side).
+template <int K, int C, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) apply_dense_lowbits_kernel(double2* __restrict__ psi,
+                                                                      const __grid_constant__ DenseArgs<K> p) {
+    constexpr int D = 1 << K, DL = 1 << C, DH = 1 << (K - C), ROW = DL + 1;
+    extern __shared__ double2 tile_all[];
+    const int lane = threadIdx.x & 31;
+    double2* T = tile_all + (threadIdx.x >> 5) * (32 * ROW);
+    const uint64_t g = uint64_t(blockIdx.x) * THREADS + threadIdx.x;
+    if (g >= p.n_items) return;  // n_items is a multiple of 32 here: whole warps leave together
+    // lane l's group starts at base0 + l * 2^C
+    double2* base0 = psi + (insert_zero_bits(g - lane, p.ins_pos, p.n_ins) | p.ctrl_mask);
+    uint64_t hstride[K - C + 1];
+#pragma unroll
+    for (int l = C; l < K; ++l) hstride[l - C] = uint64_t(1) << p.tpos[l];
+    auto hoff = [&](int h) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int l = 0; l < K - C; ++l)
+            if ((h >> l) & 1) off += hstride[l];
+        return off;
+    };
+    double2 v[D];
+    // coalesced loads: request i of run h covers amplitudes [32 i, 32 i + 32) of the run
+#pragma unroll
+    for (int h = 0; h < DH; ++h)
+#pragma unroll
+        for (int i = 0; i < DL; ++i) v[h * DL + i] = base0[hoff(h) + i * 32 + lane];
+    // transpose run by run: afterwards v[(h << C) | m] is member m of this lane's group
+#pragma unroll
+    for (int h = 0; h < DH; ++h) {
+#pragma unroll
+        for (int i = 0; i < DL; ++i) {
+            const int e = i * 32 + lane;
+            T[(e >> C) * ROW + (e & (DL - 1))] = v[h * DL + i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < DL; ++m) v[h * DL + m] = T[lane * ROW + m];
+        __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < DH; ++h) {
+#pragma unroll
+        for (int m = 0; m < DL; ++m) {
+            double re, im;
+            matvec_row<K>(p, v, (h << C) | m, re, im);
+            T[lane * ROW + m] = make_double2(re, im);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < DL; ++i) {
+            const int e = i * 32 + lane;
+            base0[hoff(h) + e] = T[(e >> C) * ROW + (e & (DL - 1))];
+        }
+        __syncwarp();
+    }
+}
+
+template <int K, int C, int THREADS, int MINB>
+static void launch_dense_lowbits(const Ctx& c, double2* psi, const DenseArgs<K>& args) {
+    constexpr int ROW = (1 << C) + 1;
+    constexpr size_t smem = size_t(THREADS / 32) * 32 * ROW * sizeof(double2);
+    static bool configured = false;
+    if (!configured) {
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(apply_dense_lowbits_kernel<K, C, THREADS, MINB>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = true;
+    }
+    const uint64_t blocks = (args.n_items + THREADS - 1) / THREADS;
+    if (blocks > 0x7fffffffULL) throw std::invalid_argument("apply_dense: grid too large");
+    apply_dense_lowbits_kernel<K, C, THREADS, MINB><<<unsigned(blocks), THREADS, smem, c.stream>>>(psi, args);
+    launched(c);
+}
+
+// number of leading target bits 0,1,2,... that qualify for the transposing kernel (0 if it does not apply)
+template <int K>
+static int lowbits_run(const DenseArgs<K>& args, int n_bits) {
+    int cbits = 0;
+    while (cbits < K && args.tpos[cbits] == cbits) ++cbits;
+    if (cbits < 2) return 0;
+    if (n_bits < cbits + 5) return 0;
+    // ins_pos is ascending and starts with the cbits low targets; the next inserted bit must leave 5 free bits above them
+    if (args.n_ins > cbits && args.ins_pos[cbits] < cbits + 5) return 0;
+    return cbits;
+}
+
 template <int K>
 static void fill_dense_args(DenseArgs<K>& args, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
                             const double* m_host) {
@@ -220,6 +311,14 @@ static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* 
     const bool bit0_target = tpos[0] == 0;
     if (bit0_target) {
         fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host);
+        if constexpr (K == 3) {
+            // Measured at 28 qubits (profiles/): k = 3 {0,1,2} 1.60 -> 1.23 ms with the transposing kernel.  At k = 4, 5 it
+            // loses (1.75 -> 1.77-2.0 ms, 3.75 -> 3.85-4.5 ms): 64+ shared-memory 128-bit operations per thread make the
+            // MIO pipe the top stall (ncu: mio_throttle, short_scoreboard), so those widths keep the 256-bit accesses.
+            const int cb = lowbits_run<K>(args, n_bits);
+            if (cb == 2) return launch_dense_lowbits<K, 2, 256, 2>(c, psi, args);
+            if (cb == 3) return launch_dense_lowbits<K, 3, 256, 2>(c, psi, args);
+        }
         launch_dense_mode<K, 1, 1, (K >= 5 ? 128 : 256), (K == 3 ? 2 : (K <= 2 ? 4 : 3))>(c, psi, args);
     } else {
         fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host);

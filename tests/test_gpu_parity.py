@@ -102,9 +102,13 @@ def test_dense_gate_every_placement_class(Backend, k):
     wf = rand_state(rng, n)
     placements = [list(range(k)), list(range(n - k, n)), sorted(int(x) for x in rng.permutation(n)[:k]),
                   [0] + list(range(n - k + 1, n))]
+    # runs of low target bits shorter than k (the warp-transposing kernel with extra high targets)
+    for c in range(2, k):
+        placements.append(list(range(c)) + list(range(n - (k - c), n)))
+        placements.append(list(range(c)) + list(range(c + 5, c + 5 + (k - c))))
     for targets in placements:
         free = [q for q in range(n) if q not in targets]
-        for ctrls in ([], [free[0]], [free[-1], free[2]], [free[1], free[5], free[-2]]):
+        for ctrls in ([], [free[0]], [free[-1], free[2]], [free[1], free[5], free[-2]], [free[-1]], [free[-3], free[-1]]):
             gpu, chk = Backend(1), OracleSimulator(1)
             for q in range(n):
                 gpu.allocate_qubit(q)

@@ -35,9 +35,11 @@ def main():
             "high": list(range(n - k, n)),
             "spread": sorted(int(x) for x in np.linspace(0, n - 1, k).round()),
             "low1_high": [0] + list(range(n - k + 1, n)),
+            "low2_high": [0, 1] + list(range(n - k + 2, n)) if k >= 3 else [0, 0],
+            "low3_high": [0, 1, 2] + list(range(n - k + 3, n)) if k >= 4 else [0, 0],
         }
         for name, pos in placements.items():
-            if len(set(pos)) != k:
+            if len(pos) != k or len(set(pos)) != k:
                 continue
             ms = sim.bench_dense_pass(m, pos, 0, 5)
             emit({"k": k, "placement": name, "pos": pos, "ms": ms, "GBs": 32.0 * amps / ms / 1e6,
