@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <set>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -373,6 +374,32 @@ void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uin
     } catch (const std::runtime_error& e) {
         throw RuntimeErr(e.what());
     }
+    // A qubit that leaves from a low local bit leaves in runs of a few bytes: the exchange then has to gather/scatter
+    // through staging slots and was measured at 240-340 GB/s per direction (bit 0: every 32-byte sector is half used),
+    // against 515-570 GB/s for the contiguous halves of a high bit.  So first move the leaving qubit onto the highest free
+    // local bit with one local pass (16 B/amplitude at HBM speed, ~25 ms on a 128 GiB shard), then exchange that bit.
+    // plan_remap has already updated loc_ as if the exchange happened at the low bit; the bookkeeping below redirects it.
+    if (L_ >= 2) {
+        std::vector<int> taken;  // local bits that take part in this remap
+        for (auto& sw : swaps) taken.push_back(sw.second);
+        int t = L_ - 1;
+        for (auto& sw : swaps) {
+            const int b = sw.second;
+            if (b >= L_ - int(swaps.size())) continue;  // already among the top bits
+            while (t >= 0 && std::find(taken.begin(), taken.end(), t) != taken.end()) --t;
+            if (t <= b) break;
+            int incoming = -1, at_t = -1;  // logical positions: the qubit plan_remap placed on b, the qubit sitting on t
+            for (int p = 0; p < n_; ++p) {
+                if (loc_[p] == b) incoming = p;
+                if (loc_[p] == t) at_t = p;
+            }
+            k::swap_local_bits(ctx(), psi(), L_, b, t);
+            if (incoming >= 0) loc_[incoming] = uint8_t(t);
+            if (at_t >= 0) loc_[at_t] = uint8_t(b);
+            sw.second = t;
+            taken.push_back(t);
+        }
+    }
     // staging: a bounded slice of the second scratch buffer (the state itself may fill most of HBM)
     const uint64_t want = std::min<uint64_t>(local_amps() >> 1, uint64_t(1) << 26);  // <= 1 GiB
     ensure_scratch(*scratch2_, std::max<uint64_t>(want, 1) * sizeof(double2));
@@ -471,6 +498,16 @@ void Engine::run_sharded() {
         return loc_[it->second] >= 64;
     };
     const int width = fusion_max_ > 0 ? fusion_max_ : 4;
+    // interaction graph of this flush (which qubits share a gate): used to break ties between eviction candidates
+    std::map<uint32_t, std::set<uint32_t>> adj;
+    for (size_t gi = 0; gi < fuser_.pending(); ++gi) {
+        const Gate& gt = fuser_.pending_gate(gi);
+        std::vector<uint32_t> qs(gt.targets);
+        qs.insert(qs.end(), gt.ctrls.begin(), gt.ctrls.end());
+        for (auto a : qs)
+            for (auto b : qs)
+                if (a != b) adj[a].insert(b);
+    }
     try {
         while (fuser_.pending() > 0) {
             std::vector<FusedPass> passes = fuser_.drain_unblocked(width, key, blocked);
@@ -481,41 +518,97 @@ void Engine::run_sharded() {
             std::vector<uint32_t> need;
             for (auto t : g.targets) need.push_back(map_.at(t));
             for (auto c : g.ctrls) need.push_back(map_.at(c));
-            std::vector<std::pair<size_t, uint32_t>> use;  // (next use, logical position) of every local qubit
-            for (auto& kv : map_)
-                if (is_local(kv.second)) use.emplace_back(fuser_.next_use(kv.first), kv.second);
-            std::sort(use.begin(), use.end(), [this](const std::pair<size_t, uint32_t>& a, const std::pair<size_t, uint32_t>& b) {
-                if (a.first != b.first) return a.first > b.first;  // needed last (or never: size_t(-1)) first
-                return loc_[a.second] > loc_[b.second];            // then the highest bit: largest contiguous blocks
-            });
-            std::vector<uint32_t> victims;
-            for (auto& u : use) victims.push_back(u.second);
             // While we are paying for an exchange, bring in the other rank-bit qubits too if they are needed sooner than
-            // the local qubits they would replace: one grouped all-to-all moves 1 - 2^-g of a shard, g separate remaps
-            // move g/2.
-            std::vector<std::pair<size_t, uint32_t>> incoming;
-            for (auto& kv : map_)
-                if (!is_local(kv.second) && std::find(need.begin(), need.end(), kv.second) == need.end())
-                    incoming.emplace_back(fuser_.next_use(kv.first), kv.second);
-            std::sort(incoming.begin(), incoming.end());
-            size_t n_global_needed = 0;
-            for (auto lp : need)
-                if (!is_local(lp)) ++n_global_needed;
-            for (auto& in : incoming) {
-                if (in.first == size_t(-1)) break;                      // never used again
-                size_t vi = n_global_needed;                             // the victim this qubit would displace
-                size_t seen = 0;
-                const std::pair<size_t, uint32_t>* victim = nullptr;
-                for (auto& u : use) {
-                    if (std::find(need.begin(), need.end(), u.second) != need.end()) continue;
-                    if (seen++ == vi) {
-                        victim = &u;
-                        break;
+            // the local qubits they would replace (plain Belady order for this decision).
+            {
+                std::vector<std::pair<size_t, uint32_t>> use0;  // (next use, logical position) of the local qubits
+                for (auto& kv : map_)
+                    if (is_local(kv.second)) use0.emplace_back(fuser_.next_use(kv.first), kv.second);
+                std::sort(use0.begin(), use0.end(),
+                          [](const std::pair<size_t, uint32_t>& a, const std::pair<size_t, uint32_t>& b) { return a.first > b.first; });
+                std::vector<std::pair<size_t, uint32_t>> incoming;
+                for (auto& kv : map_)
+                    if (!is_local(kv.second) && std::find(need.begin(), need.end(), kv.second) == need.end())
+                        incoming.emplace_back(fuser_.next_use(kv.first), kv.second);
+                std::sort(incoming.begin(), incoming.end());
+                size_t n_global_needed = 0;
+                for (auto lp : need)
+                    if (!is_local(lp)) ++n_global_needed;
+                for (auto& in : incoming) {
+                    if (in.first == size_t(-1)) break;  // never used again
+                    size_t seen = 0;
+                    const std::pair<size_t, uint32_t>* victim = nullptr;
+                    for (auto& u : use0) {
+                        if (std::find(need.begin(), need.end(), u.second) != need.end()) continue;
+                        if (seen++ == n_global_needed) {
+                            victim = &u;
+                            break;
+                        }
+                    }
+                    if (!victim || victim->first <= in.first) break;  // the local qubit is needed sooner: keep it
+                    need.push_back(in.second);
+                    ++n_global_needed;
+                }
+            }
+            // Eviction order: the local qubit needed last goes first (Belady).  Qubits that are not needed again in this
+            // flush tie; among those prefer one that shares gates with a qubit already off-device (it sits at the edge of
+            // what the off-device qubits block anyway), then the one with the fewest interaction partners, then the
+            // highest bit.  On a brickwork chain this evicts the end of the chain (q0, q1, ...) instead of a qubit in the
+            // middle, whose absence would block both directions in the next flush (simulated: 1 instead of 2 remaps per
+            // global qubit per step).
+            struct Cand {
+                size_t next_use;
+                uint32_t id, pos;
+            };
+            std::vector<Cand> cands;
+            std::set<uint32_t> off_device;  // ids on rank bits that stay there, plus victims chosen so far
+            for (auto& kv : map_) {
+                if (std::find(need.begin(), need.end(), kv.second) != need.end()) continue;
+                if (is_local(kv.second))
+                    cands.push_back({fuser_.next_use(kv.first), kv.first, kv.second});
+                else
+                    off_device.insert(kv.first);
+            }
+            std::vector<uint32_t> victims;
+            std::vector<char> picked(cands.size(), 0);
+            for (size_t round = 0; round < cands.size(); ++round) {
+                int best = -1;
+                bool best_touch = false;
+                size_t best_deg = 0;
+                for (size_t ci = 0; ci < cands.size(); ++ci) {
+                    if (picked[ci]) continue;
+                    const Cand& cd = cands[ci];
+                    bool touch = false;
+                    size_t deg = 0;
+                    auto it = adj.find(cd.id);
+                    if (it != adj.end()) {
+                        deg = it->second.size();
+                        for (auto o : it->second)
+                            if (off_device.count(o)) {
+                                touch = true;
+                                break;
+                            }
+                    }
+                    bool better;
+                    if (best < 0)
+                        better = true;
+                    else if (cd.next_use != cands[best].next_use)
+                        better = cd.next_use > cands[best].next_use;
+                    else if (touch != best_touch)
+                        better = touch;
+                    else if (deg != best_deg)
+                        better = deg < best_deg;
+                    else
+                        better = loc_[cd.pos] > loc_[cands[best].pos];
+                    if (better) {
+                        best = int(ci);
+                        best_touch = touch;
+                        best_deg = deg;
                     }
                 }
-                if (!victim || victim->first <= in.first) break;        // the local qubit is needed sooner: keep it
-                need.push_back(in.second);
-                ++n_global_needed;
+                picked[best] = 1;
+                victims.push_back(cands[best].pos);
+                off_device.insert(cands[best].id);
             }
             make_local(need, &victims);
         }

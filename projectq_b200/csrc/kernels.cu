@@ -561,6 +561,31 @@ void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices,
     launched(c);
 }
 
+// exchange two local index bits in place: psi[.., b=1, t=0, ..] <-> psi[.., b=0, t=1, ..]  (used to move a qubit that is
+// about to leave the device onto a high bit, where its half of the shard is one contiguous run)
+__global__ void __launch_bounds__(256) swap_local_bits_kernel(double2* __restrict__ psi, uint64_t n_quads, int lo, int hi) {
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t blo = uint64_t(1) << lo, bhi = uint64_t(1) << hi;
+    for (uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n_quads; g += step) {
+        const uint64_t idx = insert_zero_bit(insert_zero_bit(g, lo), hi);  // lo < hi
+        const double2 a = psi[idx | blo];
+        const double2 b = psi[idx | bhi];
+        psi[idx | blo] = b;
+        psi[idx | bhi] = a;
+    }
+}
+
+void swap_local_bits(const Ctx& c, double2* psi, int n_bits, int b0, int b1) {
+    if (b0 == b1) return;
+    const int lo = b0 < b1 ? b0 : b1, hi = b0 < b1 ? b1 : b0;
+    const uint64_t n_quads = uint64_t(1) << (n_bits - 2);
+    uint64_t blocks = (n_quads + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    swap_local_bits_kernel<<<unsigned(blocks), 256, 0, c.stream>>>(psi, n_quads, lo, hi);
+    launched(c);
+}
+
 // pack / unpack one sub-block of the shard for a global<->local qubit exchange: the sub-block is the set of amplitudes
 // whose local bits at `pos` (ascending) spell `pattern`; element j of it is shard[insert_zero_bits(j, pos) | pattern].
 // `first` is the first j of this piece, `count` its length.

@@ -45,6 +45,8 @@ void permute_gather(const Ctx& c, const double2* in, double2* out, uint64_t n_am
 // out[j] = psi[indices[j]] for a handful of indices
 void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices, uint64_t n, double2* d_out);
 
+// exchange two local index bits of the state in place (n_bits >= 2)
+void swap_local_bits(const Ctx& c, double2* psi, int n_bits, int b0, int b1);
 // remap support: gather / scatter the half of the shard whose local bit `pos` equals `value` (piece [first, first+count))
 void pack_half(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, int pos, int value);
 void unpack_half(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count, int pos, int value);
