@@ -180,6 +180,11 @@ PQB_API int pqb_host_rng_stream(uint32_t seed, size_t n, double* out);
  * (rank bit, local bit) pairs to exchange */
 PQB_API int pqb_host_plan_remap(uint8_t* loc, size_t n_logical, int n_local_bits, const uint32_t* need, size_t n_need,
                                 int32_t* out_pairs, size_t cap_pairs, size_t* out_n_pairs);
+/* dry run of the sharded scheduler (Engine::run_sharded) without a device: which fused passes run in which order and
+ * when which qubits are exchanged, for `flushes` repetitions of a gate stream on n_qubits with the top rank_bits qubits
+ * initially on rank bits.  Record layout in projectq_b200/csrc/capi.cpp. */
+PQB_API int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, uint32_t n_qubits, uint32_t rank_bits,
+                                    int max_qubits, uint32_t flushes, void* out, size_t out_cap, size_t* out_bytes);
 /* exchange plan of a (multi-bit) remap for one rank (dist.h plan_exchange): pairs = (rank bit, local bit) x n_pairs;
  * for each partner rank the pattern of exchanged local bits of the sub-block swapped with it */
 PQB_API int pqb_host_plan_exchange(int rank, const int32_t* pairs, size_t n_pairs, int32_t* out_peers, uint64_t* out_patterns,

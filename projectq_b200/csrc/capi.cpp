@@ -297,6 +297,100 @@ int pqb_host_plan_remap(uint8_t* loc, size_t n_logical, int n_local_bits, const 
     }
 }
 
+int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, uint32_t n_qubits, uint32_t rank_bits,
+                            int max_qubits, uint32_t flushes, void* out, size_t out_cap, size_t* out_bytes) {
+    // Replays Engine::run_sharded without a device: qubit ids 0..n-1 at logical positions 0..n-1, the top `rank_bits`
+    // positions on rank bits; the same gate stream is flushed `flushes` times.  Records, in order, every fused pass
+    // (u32 k, u32 nc, u32 targets[k], u32 ctrls[nc], f64 matrix[2*4^k]) and every remap (u32 0xFFFFFFFF, u32 n_pairs, then
+    // per pair u32 incoming qubit, u32 evicted qubit); a flush boundary is the record u32 0xFFFFFFFE, u32 0.
+    try {
+        if (rank_bits >= n_qubits) return PQB_ERR_VALUE;
+        const int L = int(n_qubits - rank_bits);
+        std::map<uint32_t, uint32_t> map;
+        std::vector<uint8_t> loc(n_qubits);
+        for (uint32_t p = 0; p < n_qubits; ++p) {
+            map[p] = p;
+            loc[p] = uint8_t(p < uint32_t(L) ? p : 64 + (p - L));
+        }
+        std::vector<pqb::Gate> gates;
+        const uint8_t* q = static_cast<const uint8_t*>(packed);
+        const uint8_t* end = q + n_bytes;
+        for (size_t g = 0; g < n_gates; ++g) {
+            if (q + 8 > end) return PQB_ERR_VALUE;
+            uint32_t k, nc;
+            std::memcpy(&k, q, 4);
+            std::memcpy(&nc, q + 4, 4);
+            q += 8;
+            if (k == 0 || k > 5 || nc > 64) return PQB_ERR_VALUE;
+            const size_t d = size_t(1) << k;
+            if (q + 4 * (k + nc) + 16 * d * d > end) return PQB_ERR_VALUE;
+            pqb::Gate gate;
+            gate.targets.resize(k);
+            gate.ctrls.resize(nc);
+            std::memcpy(gate.targets.data(), q, 4 * k);
+            std::memcpy(gate.ctrls.data(), q + 4 * k, 4 * nc);
+            gate.m.resize(d * d);
+            std::memcpy(gate.m.data(), q + 4 * (k + nc), 16 * d * d);
+            q += 4 * (k + nc) + 16 * d * d;
+            gates.push_back(std::move(gate));
+        }
+        uint8_t* o = static_cast<uint8_t*>(out);
+        size_t used = 0;
+        auto put = [&](const void* src, size_t n) {
+            if (used + n > out_cap) throw std::length_error("output buffer too small");
+            std::memcpy(o + used, src, n);
+            used += n;
+        };
+        auto put32 = [&](uint32_t v) { put(&v, 4); };
+        auto key = [&](uint32_t id) -> uint64_t { return loc[map.at(id)]; };
+        auto blocked = [&](uint32_t id) -> bool { return loc[map.at(id)] >= 64; };
+        pqb::Fuser fuser;
+        for (uint32_t f = 0; f < flushes; ++f) {
+            for (auto& g : gates) fuser.push(g);
+            const pqb::InteractionGraph adj = pqb::interaction_graph(fuser);
+            while (fuser.pending() > 0) {
+                auto passes = fuser.drain_unblocked(max_qubits <= 0 ? 4 : max_qubits, key, blocked);
+                for (auto& ps : passes) {
+                    const uint32_t k = uint32_t(ps.targets.size()), nc = uint32_t(ps.ctrls.size());
+                    for (auto t : ps.targets)
+                        if (loc[map.at(t)] >= 64) throw std::logic_error("scheduled a pass with an off-device target");
+                    put32(k);
+                    put32(nc);
+                    put(ps.targets.data(), 4 * k);
+                    put(ps.ctrls.data(), 4 * nc);
+                    put(ps.m.data(), 16 * (size_t(1) << k) * (size_t(1) << k));
+                }
+                if (fuser.pending() == 0) break;
+                pqb::RemapChoice choice = pqb::choose_remap(fuser, map, loc, adj);
+                std::vector<uint8_t> before = loc;
+                auto swaps = pqb::plan_remap(loc, L, choice.need, &choice.victims);
+                if (swaps.empty()) throw std::logic_error("stuck without a remap");
+                put32(0xFFFFFFFFu);
+                put32(uint32_t(swaps.size()));
+                for (auto& sw : swaps) {
+                    uint32_t in = 0, ev = 0;
+                    for (uint32_t p = 0; p < n_qubits; ++p) {
+                        if (before[p] == 64 + sw.first) in = p;
+                        if (before[p] == sw.second) ev = p;
+                    }
+                    put32(in);
+                    put32(ev);
+                }
+            }
+            put32(0xFFFFFFFEu);
+            put32(0);
+        }
+        if (out_bytes) *out_bytes = used;
+        return PQB_OK;
+    } catch (const std::length_error& e) {
+        g_create_error = e.what();
+        return PQB_ERR_MEMORY;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return PQB_ERR_RUNTIME;
+    }
+}
+
 int pqb_host_plan_exchange(int rank, const int32_t* pairs, size_t n_pairs, int32_t* out_peers, uint64_t* out_patterns,
                            size_t cap, size_t* out_n) {
     try {

@@ -97,6 +97,118 @@ std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_loc
     return swaps;
 }
 
+InteractionGraph interaction_graph(const Fuser& fuser) {
+    InteractionGraph adj;
+    for (size_t gi = 0; gi < fuser.pending(); ++gi) {
+        const Gate& gt = fuser.pending_gate(gi);
+        std::vector<uint32_t> qs(gt.targets);
+        qs.insert(qs.end(), gt.ctrls.begin(), gt.ctrls.end());
+        for (auto a : qs)
+            for (auto b : qs)
+                if (a != b) adj[a].insert(b);
+    }
+    return adj;
+}
+
+RemapChoice choose_remap(const Fuser& fuser, const std::map<uint32_t, uint32_t>& map, const std::vector<uint8_t>& loc,
+                         const InteractionGraph& adj) {
+    RemapChoice out;
+    std::vector<uint32_t>& need = out.need;
+    auto is_local = [&](uint32_t lp) { return loc[lp] < 64; };
+    auto in_need = [&](uint32_t lp) { return std::find(need.begin(), need.end(), lp) != need.end(); };
+    // the oldest waiting gate has no unfinished predecessor, so it waits for one of its own qubits
+    const Gate& g = fuser.pending_gate(0);
+    for (auto t : g.targets) need.push_back(map.at(t));
+    for (auto c : g.ctrls) need.push_back(map.at(c));
+    // While an exchange is being paid for, bring in the other rank-bit qubits too if they are needed sooner than the local
+    // qubits they would replace (plain Belady order for this decision).
+    {
+        std::vector<std::pair<size_t, uint32_t>> use0;  // (next use, logical position) of the local qubits
+        std::vector<std::pair<size_t, uint32_t>> incoming;
+        for (auto& kv : map) {
+            if (is_local(kv.second))
+                use0.emplace_back(fuser.next_use(kv.first), kv.second);
+            else if (!in_need(kv.second))
+                incoming.emplace_back(fuser.next_use(kv.first), kv.second);
+        }
+        std::sort(use0.begin(), use0.end(),
+                  [](const std::pair<size_t, uint32_t>& a, const std::pair<size_t, uint32_t>& b) { return a.first > b.first; });
+        std::sort(incoming.begin(), incoming.end());
+        size_t n_global_needed = 0;
+        for (auto lp : need)
+            if (!is_local(lp)) ++n_global_needed;
+        for (auto& in : incoming) {
+            if (in.first == size_t(-1)) break;  // never used again
+            size_t seen = 0;
+            const std::pair<size_t, uint32_t>* victim = nullptr;
+            for (auto& u : use0) {
+                if (in_need(u.second)) continue;
+                if (seen++ == n_global_needed) {
+                    victim = &u;
+                    break;
+                }
+            }
+            if (!victim || victim->first <= in.first) break;  // the local qubit is needed sooner: keep it
+            need.push_back(in.second);
+            ++n_global_needed;
+        }
+    }
+    struct Cand {
+        size_t next_use;
+        uint32_t id, pos;
+    };
+    std::vector<Cand> cands;
+    std::set<uint32_t> off_device;  // ids on rank bits that stay there, plus victims chosen so far
+    for (auto& kv : map) {
+        if (in_need(kv.second)) continue;
+        if (is_local(kv.second))
+            cands.push_back({fuser.next_use(kv.first), kv.first, kv.second});
+        else
+            off_device.insert(kv.first);
+    }
+    std::vector<char> picked(cands.size(), 0);
+    for (size_t round = 0; round < cands.size(); ++round) {
+        int best = -1;
+        bool best_touch = false;
+        size_t best_deg = 0;
+        for (size_t ci = 0; ci < cands.size(); ++ci) {
+            if (picked[ci]) continue;
+            const Cand& cd = cands[ci];
+            bool touch = false;
+            size_t deg = 0;
+            auto it = adj.find(cd.id);
+            if (it != adj.end()) {
+                deg = it->second.size();
+                for (auto o : it->second)
+                    if (off_device.count(o)) {
+                        touch = true;
+                        break;
+                    }
+            }
+            bool better;
+            if (best < 0)
+                better = true;
+            else if (cd.next_use != cands[best].next_use)
+                better = cd.next_use > cands[best].next_use;
+            else if (touch != best_touch)
+                better = touch;
+            else if (deg != best_deg)
+                better = deg < best_deg;
+            else
+                better = loc[cd.pos] > loc[cands[best].pos];
+            if (better) {
+                best = int(ci);
+                best_touch = touch;
+                best_deg = deg;
+            }
+        }
+        picked[best] = 1;
+        out.victims.push_back(cands[best].pos);
+        off_device.insert(cands[best].id);
+    }
+    return out;
+}
+
 std::vector<ExchangePeer> plan_exchange(int rank, const std::vector<std::pair<int, int>>& swaps) {
     std::vector<ExchangePeer> out;
     const int g = int(swaps.size());

@@ -9,7 +9,11 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
+#include <set>
 #include <vector>
+
+#include "fuser.h"
 
 namespace pqb {
 
@@ -20,6 +24,21 @@ namespace pqb {
 // `victims` (optional) lists logical positions in eviction-preference order (the engine passes "needed last" first).
 std::vector<std::pair<int, int>> plan_remap(std::vector<uint8_t>& loc, int n_local_bits, const std::vector<uint32_t>& need,
                                             const std::vector<uint32_t>* victims = nullptr);
+
+// ---- when to remap and whom to evict (pure host logic, driven by Engine::run_sharded and, for CPU tests, by
+// pqb_host_shard_schedule) ----------------------------------------------------------------------------------------------
+using InteractionGraph = std::map<uint32_t, std::set<uint32_t>>;  // qubit id -> ids it shares a gate with
+InteractionGraph interaction_graph(const Fuser& fuser);
+struct RemapChoice {
+    std::vector<uint32_t> need;     // logical positions that must be on-device next
+    std::vector<uint32_t> victims;  // local logical positions in eviction-preference order
+};
+// Called when every pending gate waits for a qubit on a rank bit.  need = the qubits of the oldest waiting gate, plus the
+// other rank-bit qubits that are needed sooner than the local qubits they would displace.  Eviction order: needed last
+// first (Belady); ties (not needed again in this flush) go to a qubit that shares gates with a qubit already off-device,
+// then to the one with the fewest interaction partners, then to the highest bit.
+RemapChoice choose_remap(const Fuser& fuser, const std::map<uint32_t, uint32_t>& id_to_logical,
+                         const std::vector<uint8_t>& loc, const InteractionGraph& adj);
 
 // Who exchanges what in a (multi-bit) remap.  Exchanging rank bits r_i with local bits b_i sends, from every rank, the
 // sub-block whose local bits (b_i) spell beta to the rank whose bits (r_i) spell beta, and the sub-block that arrives from

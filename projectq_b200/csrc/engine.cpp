@@ -498,118 +498,15 @@ void Engine::run_sharded() {
         return loc_[it->second] >= 64;
     };
     const int width = fusion_max_ > 0 ? fusion_max_ : 4;
-    // interaction graph of this flush (which qubits share a gate): used to break ties between eviction candidates
-    std::map<uint32_t, std::set<uint32_t>> adj;
-    for (size_t gi = 0; gi < fuser_.pending(); ++gi) {
-        const Gate& gt = fuser_.pending_gate(gi);
-        std::vector<uint32_t> qs(gt.targets);
-        qs.insert(qs.end(), gt.ctrls.begin(), gt.ctrls.end());
-        for (auto a : qs)
-            for (auto b : qs)
-                if (a != b) adj[a].insert(b);
-    }
+    const InteractionGraph adj = interaction_graph(fuser_);  // of this flush: breaks ties between eviction candidates
     try {
         while (fuser_.pending() > 0) {
             std::vector<FusedPass> passes = fuser_.drain_unblocked(width, key, blocked);
             for (auto& p : passes) apply_pass(p);
             if (fuser_.pending() == 0) break;
-            // the oldest waiting gate has no unfinished predecessor, so it waits for one of its own qubits
-            const Gate& g = fuser_.pending_gate(0);
-            std::vector<uint32_t> need;
-            for (auto t : g.targets) need.push_back(map_.at(t));
-            for (auto c : g.ctrls) need.push_back(map_.at(c));
-            // While we are paying for an exchange, bring in the other rank-bit qubits too if they are needed sooner than
-            // the local qubits they would replace (plain Belady order for this decision).
-            {
-                std::vector<std::pair<size_t, uint32_t>> use0;  // (next use, logical position) of the local qubits
-                for (auto& kv : map_)
-                    if (is_local(kv.second)) use0.emplace_back(fuser_.next_use(kv.first), kv.second);
-                std::sort(use0.begin(), use0.end(),
-                          [](const std::pair<size_t, uint32_t>& a, const std::pair<size_t, uint32_t>& b) { return a.first > b.first; });
-                std::vector<std::pair<size_t, uint32_t>> incoming;
-                for (auto& kv : map_)
-                    if (!is_local(kv.second) && std::find(need.begin(), need.end(), kv.second) == need.end())
-                        incoming.emplace_back(fuser_.next_use(kv.first), kv.second);
-                std::sort(incoming.begin(), incoming.end());
-                size_t n_global_needed = 0;
-                for (auto lp : need)
-                    if (!is_local(lp)) ++n_global_needed;
-                for (auto& in : incoming) {
-                    if (in.first == size_t(-1)) break;  // never used again
-                    size_t seen = 0;
-                    const std::pair<size_t, uint32_t>* victim = nullptr;
-                    for (auto& u : use0) {
-                        if (std::find(need.begin(), need.end(), u.second) != need.end()) continue;
-                        if (seen++ == n_global_needed) {
-                            victim = &u;
-                            break;
-                        }
-                    }
-                    if (!victim || victim->first <= in.first) break;  // the local qubit is needed sooner: keep it
-                    need.push_back(in.second);
-                    ++n_global_needed;
-                }
-            }
-            // Eviction order: the local qubit needed last goes first (Belady).  Qubits that are not needed again in this
-            // flush tie; among those prefer one that shares gates with a qubit already off-device (it sits at the edge of
-            // what the off-device qubits block anyway), then the one with the fewest interaction partners, then the
-            // highest bit.  On a brickwork chain this evicts the end of the chain (q0, q1, ...) instead of a qubit in the
-            // middle, whose absence would block both directions in the next flush (simulated: 1 instead of 2 remaps per
-            // global qubit per step).
-            struct Cand {
-                size_t next_use;
-                uint32_t id, pos;
-            };
-            std::vector<Cand> cands;
-            std::set<uint32_t> off_device;  // ids on rank bits that stay there, plus victims chosen so far
-            for (auto& kv : map_) {
-                if (std::find(need.begin(), need.end(), kv.second) != need.end()) continue;
-                if (is_local(kv.second))
-                    cands.push_back({fuser_.next_use(kv.first), kv.first, kv.second});
-                else
-                    off_device.insert(kv.first);
-            }
-            std::vector<uint32_t> victims;
-            std::vector<char> picked(cands.size(), 0);
-            for (size_t round = 0; round < cands.size(); ++round) {
-                int best = -1;
-                bool best_touch = false;
-                size_t best_deg = 0;
-                for (size_t ci = 0; ci < cands.size(); ++ci) {
-                    if (picked[ci]) continue;
-                    const Cand& cd = cands[ci];
-                    bool touch = false;
-                    size_t deg = 0;
-                    auto it = adj.find(cd.id);
-                    if (it != adj.end()) {
-                        deg = it->second.size();
-                        for (auto o : it->second)
-                            if (off_device.count(o)) {
-                                touch = true;
-                                break;
-                            }
-                    }
-                    bool better;
-                    if (best < 0)
-                        better = true;
-                    else if (cd.next_use != cands[best].next_use)
-                        better = cd.next_use > cands[best].next_use;
-                    else if (touch != best_touch)
-                        better = touch;
-                    else if (deg != best_deg)
-                        better = deg < best_deg;
-                    else
-                        better = loc_[cd.pos] > loc_[cands[best].pos];
-                    if (better) {
-                        best = int(ci);
-                        best_touch = touch;
-                        best_deg = deg;
-                    }
-                }
-                picked[best] = 1;
-                victims.push_back(cands[best].pos);
-                off_device.insert(cands[best].id);
-            }
+            RemapChoice choice = choose_remap(fuser_, map_, loc_, adj);
+            const std::vector<uint32_t>& need = choice.need;
+            const std::vector<uint32_t>& victims = choice.victims;
             make_local(need, &victims);
         }
     } catch (...) {

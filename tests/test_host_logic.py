@@ -212,3 +212,81 @@ def test_exchange_plan_is_the_bit_swap_permutation(lib):
                     er = (er & ~(1 << r)) | (lb << r)
                     el = (el & ~(1 << b)) | (rb << b)
                 assert (er, el) == (rank, local)
+
+
+def shard_schedule(lib, gates, n, rank_bits, flushes, max_qubits=4):
+    body, cnt = pack_gate_stream(gates)
+    cap = (len(body) * 8 + (1 << 20)) * flushes
+    out = ctypes.create_string_buffer(cap)
+    used = ctypes.c_size_t()
+    st = lib.pqb_host_shard_schedule(body, ctypes.c_size_t(len(body)), ctypes.c_size_t(cnt), ctypes.c_uint32(n),
+                                     ctypes.c_uint32(rank_bits), ctypes.c_int(max_qubits), ctypes.c_uint32(flushes), out,
+                                     ctypes.c_size_t(cap), ctypes.byref(used))
+    lib.pqb_last_error.restype = ctypes.c_char_p
+    assert st == 0, lib.pqb_last_error(None)
+    raw = out.raw[: used.value]
+    events, off = [], 0
+    while off < len(raw):
+        k, nc = (int(x) for x in np.frombuffer(raw, dtype=np.uint32, count=2, offset=off))
+        off += 8
+        if k == 0xFFFFFFFF:
+            pairs = np.frombuffer(raw, dtype=np.uint32, count=2 * nc, offset=off).reshape(nc, 2)
+            off += 8 * nc
+            events.append(("remap", [(int(a), int(b)) for a, b in pairs]))
+        elif k == 0xFFFFFFFE:
+            events.append(("flush", None))
+        else:
+            ids = np.frombuffer(raw, dtype=np.uint32, count=k + nc, offset=off)
+            off += 4 * (k + nc)
+            d = 1 << k
+            m = np.frombuffer(raw, dtype=np.complex128, count=d * d, offset=off).reshape(d, d)
+            off += 16 * d * d
+            events.append(("pass", (m, [int(x) for x in ids[:k]], [int(x) for x in ids[k:]])))
+    return events
+
+
+@pytest.mark.parametrize("rank_bits", [1, 2, 3])
+def test_sharded_schedule_is_equivalent_and_remaps_once_per_global_qubit(lib, rank_bits):
+    """dry run of Engine::run_sharded: deferring the gates on off-device qubits must not change the circuit, every
+    scheduled pass must act on on-device qubits only, and a brickwork flush needs one exchange per global qubit"""
+    n, depth, flushes = 16, 6, 4  # depth well below n: one sweep of the chain per flush is possible
+    gates = brickwork_circuit(n, depth, seed=21)
+    events = shard_schedule(lib, gates, n, rank_bits, flushes)
+    off_device = set(range(n - rank_bits, n))
+    passes, remaps_per_flush, cur = [], [], 0
+    for kind, payload in events:
+        if kind == "pass":
+            m, t, c = payload
+            assert not (set(t) & off_device), "a dense target is off-device"
+            passes.append(payload)
+        elif kind == "remap":
+            for incoming, evicted in payload:
+                assert incoming in off_device and evicted not in off_device
+                off_device.remove(incoming)
+                off_device.add(evicted)
+            cur += len(payload)
+        else:
+            remaps_per_flush.append(cur)
+            cur = 0
+    assert len(remaps_per_flush) == flushes
+    assert all(r <= rank_bits for r in remaps_per_flush[1:]), remaps_per_flush  # steady state: one per global qubit
+    assert remaps_per_flush[0] <= 2 * rank_bits
+    wf = rand_state(np.random.default_rng(3), n)
+    want = run_oracle(n, wf, gates * flushes)
+    got = run_oracle(n, wf, passes)
+    assert np.max(np.abs(want - got)) < 1e-12
+
+
+def test_sharded_schedule_random_circuit(lib):
+    rng = np.random.default_rng(77)
+    n = 10
+    gates = []
+    for g in range(120):
+        k = int(rng.integers(1, 4))
+        nc = int(rng.integers(0, 3))
+        qs = [int(x) for x in rng.permutation(n)[: k + nc]]
+        gates.append((rand_unitary(rng, k), qs[:k], qs[k:]))
+    events = shard_schedule(lib, gates, n, 3, 2, max_qubits=5)
+    passes = [p for kind, p in events if kind == "pass"]
+    wf = rand_state(rng, n)
+    assert np.max(np.abs(run_oracle(n, wf, gates * 2) - run_oracle(n, wf, passes))) < 1e-12
