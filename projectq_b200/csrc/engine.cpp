@@ -292,6 +292,9 @@ void Engine::apply_controlled_gate(const double* m, const uint32_t* ids, size_t 
     Gate g;
     g.targets.assign(ids, ids + k);
     g.ctrls.assign(ctrl, ctrl + nc);
+    // a control listed twice is one control (the reference ORs the positions into a mask, simulator.hpp:551-556)
+    std::sort(g.ctrls.begin(), g.ctrls.end());
+    g.ctrls.erase(std::unique(g.ctrls.begin(), g.ctrls.end()), g.ctrls.end());
     for (size_t i = 0; i < k; ++i) {
         for (size_t j = i + 1; j < k; ++j)
             if (ids[i] == ids[j]) throw ValueErr("apply_controlled_gate(): duplicate target qubit");
