@@ -448,7 +448,6 @@ void Engine::run() {
         run_sharded();
         return;
     }
-    // every id must be known before positions are resolved (the reference would silently insert into map_)
     // sort key of a qubit inside a pass = its physical place; rank bits sort above all local bits
     auto key = [this](uint32_t id) -> uint64_t {
         auto it = map_.find(id);
@@ -458,32 +457,40 @@ void Engine::run() {
     // Relative cost of one pass by width, measured on B200 (profiles/): k <= 4 runs at the HBM roofline (32 B/amplitude),
     // k = 5 is bound by the FP64 pipe (256 flop/amplitude) and takes ~2.4x as long, so a 5-wide pass only pays off when
     // it swallows that many more gates.  A control bit halves the amplitudes a pass touches.
-    auto cost = [](const std::vector<FusedPass>& ps) {
+    auto cost = [](const std::vector<Cluster>& cs) {
         double c = 0.0;
-        for (auto& p : ps) {
-            double w = (!p.diagonal && p.targets.size() >= 5) ? 2.4 : 1.0;
-            for (size_t i = 0; i < p.ctrls.size() && i < 6; ++i) w *= 0.5;
+        for (auto& cl : cs) {
+            double w = cl.width >= 5 ? 2.4 : 1.0;
+            for (int i = 0; i < cl.n_ctrl && i < 6; ++i) w *= 0.5;
             c += w + 0.002;  // + launch overhead so tiny states prefer fewer passes
         }
         return c;
     };
-    std::vector<FusedPass> passes;
     try {
-        if (fusion_max_ > 0) {
-            passes = fuser_.drain(fusion_max_, key);
-        } else {
-            passes = fuser_.plan(4, key);
-            if (passes.size() > 1) {
-                auto wide = fuser_.plan(5, key);
-                if (cost(wide) < cost(passes)) passes.swap(wide);
-            }
-            fuser_.clear();
+        // every id must be known before anything is applied (the reference would silently insert into map_)
+        for (size_t gi = 0; gi < fuser_.pending(); ++gi) {
+            const Gate& gt = fuser_.pending_gate(gi);
+            for (auto t : gt.targets) key(t);
+            for (auto c : gt.ctrls) key(c);
         }
+        // schedule first (no matrix products), then fuse and launch pass by pass: the GPU runs pass i while the host
+        // builds the matrix of pass i+1
+        std::vector<Cluster> clusters;
+        if (fusion_max_ > 0) {
+            clusters = fuser_.schedule(fusion_max_);
+        } else {
+            clusters = fuser_.schedule(4);
+            if (clusters.size() > 1) {
+                std::vector<Cluster> wide = fuser_.schedule(5);
+                if (cost(wide) < cost(clusters)) clusters.swap(wide);
+            }
+        }
+        for (auto& cl : clusters) apply_pass(fuser_.fuse_cluster(cl, key));
+        fuser_.clear();
     } catch (...) {
         fuser_.clear();  // never leave a poisoned queue behind (the reference does, simulator.hpp:522-526)
         throw;
     }
-    for (auto& p : passes) apply_pass(p);
 }
 
 // Sharded run(): execute everything that touches only on-device qubits, and only then pay for a remap.  The remap brings
@@ -504,8 +511,10 @@ void Engine::run_sharded() {
     const InteractionGraph adj = interaction_graph(fuser_);  // of this flush: breaks ties between eviction candidates
     try {
         while (fuser_.pending() > 0) {
-            std::vector<FusedPass> passes = fuser_.drain_unblocked(width, key, blocked);
-            for (auto& p : passes) apply_pass(p);
+            std::vector<char> done;
+            const std::vector<Cluster> clusters = fuser_.schedule_unblocked(width, blocked, done);
+            for (auto& cl : clusters) apply_pass(fuser_.fuse_cluster(cl, key));
+            fuser_.remove_done(done);
             if (fuser_.pending() == 0) break;
             RemapChoice choice = choose_remap(fuser_, map_, loc_, adj);
             const std::vector<uint32_t>& need = choice.need;

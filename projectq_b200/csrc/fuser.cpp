@@ -167,17 +167,41 @@ std::vector<FusedPass> Fuser::drain(int max_qubits, const std::function<uint64_t
 
 std::vector<FusedPass> Fuser::plan(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key) const {
     std::vector<char> done;
-    return plan_impl(max_qubits, sort_key, nullptr, done);
+    std::vector<FusedPass> passes;
+    for (auto& cl : schedule_impl(max_qubits, nullptr, done)) passes.push_back(fuse_cluster(cl, sort_key));
+    return passes;
+}
+
+std::vector<Cluster> Fuser::schedule(int max_qubits) const {
+    std::vector<char> done;
+    return schedule_impl(max_qubits, nullptr, done);
+}
+
+std::vector<Cluster> Fuser::schedule_unblocked(int max_qubits, const std::function<bool(uint32_t)>& blocked,
+                                               std::vector<char>& done) const {
+    return schedule_impl(max_qubits, &blocked, done);
+}
+
+FusedPass Fuser::fuse_cluster(const Cluster& cl, const std::function<uint64_t(uint32_t)>& sort_key) const {
+    std::vector<const Gate*> members;
+    members.reserve(cl.gates.size());
+    for (auto g : cl.gates) members.push_back(&pending_[g]);
+    return fuse(members, sort_key);
+}
+
+void Fuser::remove_done(const std::vector<char>& done) {
+    std::vector<Gate> rest;
+    for (size_t g = 0; g < pending_.size(); ++g)
+        if (g >= done.size() || !done[g]) rest.push_back(std::move(pending_[g]));
+    pending_.swap(rest);
 }
 
 std::vector<FusedPass> Fuser::drain_unblocked(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key,
                                               const std::function<bool(uint32_t)>& blocked) {
     std::vector<char> done;
-    std::vector<FusedPass> passes = plan_impl(max_qubits, sort_key, &blocked, done);
-    std::vector<Gate> rest;
-    for (size_t g = 0; g < pending_.size(); ++g)
-        if (!done[g]) rest.push_back(std::move(pending_[g]));
-    pending_.swap(rest);
+    std::vector<FusedPass> passes;
+    for (auto& cl : schedule_impl(max_qubits, &blocked, done)) passes.push_back(fuse_cluster(cl, sort_key));
+    remove_done(done);
     return passes;
 }
 
@@ -188,9 +212,9 @@ size_t Fuser::next_use(uint32_t id) const {
     return size_t(-1);
 }
 
-std::vector<FusedPass> Fuser::plan_impl(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key,
-                                        const std::function<bool(uint32_t)>* blocked, std::vector<char>& done) const {
-    std::vector<FusedPass> passes;
+std::vector<Cluster> Fuser::schedule_impl(int max_qubits, const std::function<bool(uint32_t)>* blocked,
+                                          std::vector<char>& done) const {
+    std::vector<Cluster> passes;
     const size_t m = pending_.size();
     done.assign(m, 0);
     if (m == 0) return passes;
@@ -236,7 +260,7 @@ std::vector<FusedPass> Fuser::plan_impl(int max_qubits, const std::function<uint
 
     size_t first = 0;
     std::vector<uint32_t> S, G;
-    std::vector<const Gate*> members;
+    std::vector<uint32_t> members;
     while (true) {
         while (first < m && done[first]) ++first;
         if (first >= m) break;
@@ -255,7 +279,7 @@ std::vector<FusedPass> Fuser::plan_impl(int max_qubits, const std::function<uint
         S.clear();
         G.clear();
         absorb(S, G, pending_[seed], true);
-        members.push_back(&pending_[seed]);
+        members.push_back(uint32_t(seed));
         done[seed] = 1;
         // grow the pass: prefer gates that fit without widening it, then the smallest widening, then program order
         while (true) {
@@ -275,10 +299,10 @@ std::vector<FusedPass> Fuser::plan_impl(int max_qubits, const std::function<uint
             }
             if (best == m) break;
             absorb(S, G, pending_[best], false);
-            members.push_back(&pending_[best]);
+            members.push_back(uint32_t(best));
             done[best] = 1;
         }
-        passes.push_back(fuse(members, sort_key));
+        passes.push_back(Cluster{members, int(S.size()), int(G.size())});
     }
     return passes;
 }

@@ -31,6 +31,13 @@ struct FusedPass {
     bool diagonal = false;          // every off-diagonal entry is exactly zero
 };
 
+// one scheduled pass before its matrix is built: which pending gates it contains, its width and common controls
+struct Cluster {
+    std::vector<uint32_t> gates;  // indices into the pending queue, in application order
+    int width = 0;
+    int n_ctrl = 0;
+};
+
 class Fuser {
 public:
     void push(Gate g) { pending_.push_back(std::move(g)); }
@@ -42,6 +49,14 @@ public:
     std::vector<FusedPass> drain(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key);
     // Same schedule, but the pending gates stay queued (used to compare fusion widths before committing to one).
     std::vector<FusedPass> plan(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key) const;
+
+    // Two-step form used by the engine: schedule first (cheap: no matrix products), then build and launch one pass at a
+    // time, so that the GPU works on pass i while the host multiplies the matrices of pass i+1.
+    std::vector<Cluster> schedule(int max_qubits) const;
+    std::vector<Cluster> schedule_unblocked(int max_qubits, const std::function<bool(uint32_t)>& blocked,
+                                            std::vector<char>& done) const;
+    FusedPass fuse_cluster(const Cluster& cl, const std::function<uint64_t(uint32_t)>& sort_key) const;
+    void remove_done(const std::vector<char>& done);  // drop the gates a schedule_unblocked call marked
 
     // Sharded runs: schedule (and remove from the queue) only what can run without touching a blocked qubit; gates that
     // touch one, and everything that depends on them, stay queued in program order.
@@ -59,8 +74,8 @@ public:
     static void reorder(FusedPass& p, const std::function<uint64_t(uint32_t)>& sort_key);
 
 private:
-    std::vector<FusedPass> plan_impl(int max_qubits, const std::function<uint64_t(uint32_t)>& sort_key,
-                                     const std::function<bool(uint32_t)>* blocked, std::vector<char>& done) const;
+    std::vector<Cluster> schedule_impl(int max_qubits, const std::function<bool(uint32_t)>* blocked,
+                                       std::vector<char>& done) const;
     std::vector<Gate> pending_;
 };
 
