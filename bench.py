@@ -94,11 +94,15 @@ def reference_sample(n_qubits, steps, warmup):
     """time the unmodified reference C++ simulator on the same generator at n_qubits; returns (best amp-updates/s, info)"""
     from tests.conftest import load_ref_cppsim
 
+    # the reference is an OpenMP code: give it every host core (torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # would silently turn the baseline into a single-thread run); libgomp reads this when the module is first loaded
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")  # the reference's own advice, _simulator.py:50-55
     mod = load_ref_cppsim()
     if mod is None:
         return None, "oracle/_ref/_cppsim not built"
     gates = [(m.tolist(), t, c) for m, t, c in brickwork_circuit(n_qubits, DEPTH)]
-    cores = os.cpu_count() or 1
     best = {}
     for fusion in (False, True):
         sim = mod.Simulator(1)
