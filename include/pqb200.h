@@ -72,7 +72,8 @@ typedef struct pqb_stats {
     uint64_t remap_bytes_sent;    /* bytes this rank sent over NVLink in remaps */
     double remap_ms;              /* device time spent in remaps */
     uint64_t diag_passes;         /* passes applied by the diagonal kernel */
-    uint64_t reserved_[7];
+    uint64_t p2p_remaps;          /* remaps done by the peer-memory exchange kernel (opt-in) rather than NCCL send/recv */
+    uint64_t reserved_[6];
 } pqb_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------ */
@@ -185,6 +186,9 @@ PQB_API int pqb_host_plan_remap(uint8_t* loc, size_t n_logical, int n_local_bits
  * initially on rank bits.  Record layout in projectq_b200/csrc/capi.cpp. */
 PQB_API int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, uint32_t n_qubits, uint32_t rank_bits,
                                     int max_qubits, uint32_t flushes, void* out, size_t out_cap, size_t* out_bytes);
+/* self-test of the descriptor channel between rank processes (projectq_b200/csrc/fdpass.h): call from `world` processes
+ * with the same run_tag; every pair exchanges a pipe descriptor and checks its content */
+PQB_API int pqb_host_fdpass_selftest(uint64_t run_tag, int rank, int world);
 /* exchange plan of a (multi-bit) remap for one rank (dist.h plan_exchange): pairs = (rank bit, local bit) x n_pairs;
  * for each partner rank the pattern of exchanged local bits of the sub-block swapped with it */
 PQB_API int pqb_host_plan_exchange(int rank, const int32_t* pairs, size_t n_pairs, int32_t* out_peers, uint64_t* out_patterns,

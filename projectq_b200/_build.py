@@ -15,8 +15,8 @@ LIB = os.path.join(HERE, "libpqb200.so")
 SHIM = os.path.join(HERE, "_pqb_shim" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-LIB_SOURCES = ["kernels.cu", "engine.cpp", "fuser.cpp", "devmem.cpp", "dist.cpp", "capi.cpp"]
-LIB_HEADERS = ["kernels.cuh", "engine.h", "fuser.h", "devmem.h", "dist.h", "bits.h", "../../include/pqb200.h"]
+LIB_SOURCES = ["kernels.cu", "engine.cpp", "fuser.cpp", "devmem.cpp", "dist.cpp", "fdpass.cpp", "capi.cpp"]
+LIB_HEADERS = ["kernels.cuh", "engine.h", "fuser.h", "devmem.h", "dist.h", "fdpass.h", "bits.h", "../../include/pqb200.h"]
 
 
 def _stale(target, deps):

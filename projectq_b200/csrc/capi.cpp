@@ -4,8 +4,11 @@
 #include <new>
 #include <string>
 
+#include <unistd.h>
+
 #include "dist.h"
 #include "engine.h"
+#include "fdpass.h"
 
 using pqb::Engine;
 
@@ -385,6 +388,40 @@ int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, 
     } catch (const std::length_error& e) {
         g_create_error = e.what();
         return PQB_ERR_MEMORY;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return PQB_ERR_RUNTIME;
+    }
+}
+
+int pqb_host_fdpass_selftest(uint64_t run_tag, int rank, int world) {
+    // every rank hands every other rank the read end of a pipe that holds (rank * 1000 + peer) and checks what it gets
+    try {
+        pqb::FdChannel ch(run_tag, rank);
+        for (int k = 1; k < world; ++k) {
+            const int peer = rank ^ k;
+            if (peer >= world) continue;
+            int fds[2];
+            if (::pipe(fds) != 0) return PQB_ERR_RUNTIME;
+            const int32_t token = rank * 1000 + peer;
+            if (::write(fds[1], &token, sizeof(token)) != ssize_t(sizeof(token))) return PQB_ERR_RUNTIME;
+            ::close(fds[1]);
+            const int32_t me = rank;
+            ch.send(peer, &me, sizeof(me), {fds[0]});
+            ::close(fds[0]);
+            int32_t who = -1;
+            std::vector<int> got;
+            ch.recv(peer, &who, sizeof(who), got, 1);
+            int32_t seen = -1;
+            const bool ok = who == peer && ::read(got[0], &seen, sizeof(seen)) == ssize_t(sizeof(seen)) &&
+                            seen == peer * 1000 + rank;
+            ::close(got[0]);
+            if (!ok) {
+                g_create_error = "fdpass selftest: wrong token";
+                return PQB_ERR_RUNTIME;
+            }
+        }
+        return PQB_OK;
     } catch (const std::exception& e) {
         g_create_error = e.what();
         return PQB_ERR_RUNTIME;

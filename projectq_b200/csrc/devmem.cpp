@@ -3,6 +3,9 @@
 
 #include <cuda.h>
 
+#include <unistd.h>
+
+#include <cstdlib>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -21,6 +24,9 @@ struct DriverApi {
     CUresult (*memUnmap)(CUdeviceptr, size_t) = nullptr;
     CUresult (*memSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
     CUresult (*memGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*memExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType,
+                                           unsigned long long) = nullptr;
+    CUresult (*memImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
 };
 
 template <class F>
@@ -42,6 +48,12 @@ const DriverApi& driver() {
                fetch("cuMemCreate", a.memCreate) && fetch("cuMemRelease", a.memRelease) && fetch("cuMemMap", a.memMap) &&
                fetch("cuMemUnmap", a.memUnmap) && fetch("cuMemSetAccess", a.memSetAccess) &&
                fetch("cuMemGetAllocationGranularity", a.memGetAllocationGranularity);
+        // optional: sharing a buffer with a partner process
+        if (!(fetch("cuMemExportToShareableHandle", a.memExportToShareableHandle) &&
+              fetch("cuMemImportFromShareableHandle", a.memImportFromShareableHandle))) {
+            a.memExportToShareableHandle = nullptr;
+            a.memImportFromShareableHandle = nullptr;
+        }
         return a;
     }();
     return api;
@@ -52,6 +64,13 @@ CUmemAllocationProp alloc_prop(int device) {
     prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
     prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     prop.location.id = device;
+    // exportable chunks (so that a partner rank can map the shard) only when the peer-memory remap path is switched on:
+    // the default allocation path stays exactly the one the round-1 measurements were taken with
+    static const bool exportable = [] {
+        const char* e = getenv("PQB_REMAP_P2P");
+        return e && e[0] == '1';
+    }();
+    if (exportable) prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
     return prop;
 }
 
@@ -91,7 +110,10 @@ void GrowBuffer::ensure(size_t bytes) {
         const size_t add = round_up(bytes - mapped_, gran_);
         CUmemAllocationProp prop = alloc_prop(device_);
         CUmemGenericAllocationHandle h = 0;
-        if (d.memCreate(&h, add, &prop, 0) != CUDA_SUCCESS) throw std::bad_alloc();
+        if (d.memCreate(&h, add, &prop, 0) != CUDA_SUCCESS) {
+            prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_NONE;  // not exportable here: still usable locally
+            if (d.memCreate(&h, add, &prop, 0) != CUDA_SUCCESS) throw std::bad_alloc();
+        }
         if (d.memMap(base_ + mapped_, add, 0, h, 0) != CUDA_SUCCESS) {
             d.memRelease(h);
             throw std::bad_alloc();
@@ -143,6 +165,78 @@ void GrowBuffer::shrink_to(size_t bytes) {
         base_ = 0;
         mapped_ = 0;
     }
+}
+
+bool GrowBuffer::export_chunks(std::vector<int>& fds, std::vector<size_t>& sizes) const {
+    fds.clear();
+    sizes.clear();
+    const DriverApi& d = driver();
+    if (!vmm_ || !d.memExportToShareableHandle) return false;
+    for (auto& ch : chunks_) {
+        int fd = -1;
+        if (d.memExportToShareableHandle(&fd, ch.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS || fd < 0) {
+            for (int f : fds) ::close(f);
+            fds.clear();
+            sizes.clear();
+            return false;
+        }
+        fds.push_back(fd);
+        sizes.push_back(ch.size);
+    }
+    return true;
+}
+
+void PeerMapping::map(int device, const std::vector<int>& fds, const std::vector<size_t>& sizes) {
+    reset();
+    const DriverApi& d = driver();
+    if (!d.ok || !d.memImportFromShareableHandle) throw std::runtime_error("peer mapping: driver API unavailable");
+    size_t total = 0;
+    for (auto s : sizes) total += s;
+    CUdeviceptr base = 0;
+    if (d.memAddressReserve(&base, total, 0, 0, 0) != CUDA_SUCCESS) throw std::runtime_error("peer mapping: reserve failed");
+    base_ = base;
+    va_size_ = total;
+    size_t off = 0;
+    for (size_t i = 0; i < fds.size(); ++i) {
+        CUmemGenericAllocationHandle h = 0;
+        if (d.memImportFromShareableHandle(&h, reinterpret_cast<void*>(static_cast<uintptr_t>(fds[i])),
+                                           CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS) {
+            reset();
+            throw std::runtime_error("peer mapping: import failed");
+        }
+        if (d.memMap(base_ + off, sizes[i], 0, h, 0) != CUDA_SUCCESS) {
+            d.memRelease(h);
+            reset();
+            throw std::runtime_error("peer mapping: map failed");
+        }
+        handles_.emplace_back(h, sizes[i]);
+        off += sizes[i];
+        total_ = off;
+    }
+    CUmemAccessDesc acc = {};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (d.memSetAccess(base_, total_, &acc, 1) != CUDA_SUCCESS) {
+        reset();
+        throw std::runtime_error("peer mapping: no peer access between the two devices");
+    }
+}
+
+void PeerMapping::reset() {
+    if (!base_) return;
+    const DriverApi& d = driver();
+    cudaDeviceSynchronize();
+    size_t off = 0;
+    for (auto& h : handles_) {
+        d.memUnmap(base_ + off, h.second);
+        d.memRelease(h.first);
+        off += h.second;
+    }
+    handles_.clear();
+    d.memAddressFree(base_, va_size_);
+    base_ = 0;
+    total_ = va_size_ = 0;
 }
 
 GrowBuffer::~GrowBuffer() {

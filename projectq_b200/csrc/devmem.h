@@ -29,6 +29,12 @@ public:
     void shrink_to(size_t bytes);
     void release() { shrink_to(0); }
 
+    // Export every mapped chunk as a POSIX file descriptor (caller closes them) so that a partner process can map the
+    // buffer (PeerMapping).  Returns false when the buffer is not a VMM allocation or the driver refuses.
+    bool export_chunks(std::vector<int>& fds, std::vector<size_t>& sizes) const;
+    // changes whenever the address range or the set of chunks changes (a partner's mapping is then stale)
+    uint64_t layout_key() const { return base_ * 1315423911ULL + mapped_ * 2654435761ULL + chunks_.size(); }
+
     void* ptr() const { return reinterpret_cast<void*>(base_); }
     double2* amps() const { return reinterpret_cast<double2*>(base_); }
     size_t capacity() const { return mapped_; }
@@ -47,6 +53,25 @@ private:
     size_t mapped_ = 0;
     size_t gran_ = 0;
     std::vector<Chunk> chunks_;
+};
+
+// A partner rank's buffer mapped into this process (peer access over NVLink) from the descriptors of its chunks.
+class PeerMapping {
+public:
+    PeerMapping() = default;
+    ~PeerMapping() { reset(); }
+    PeerMapping(const PeerMapping&) = delete;
+    PeerMapping& operator=(const PeerMapping&) = delete;
+    // import the chunks (descriptors stay owned by the caller), map them back to back, grant `device` read/write access
+    void map(int device, const std::vector<int>& fds, const std::vector<size_t>& sizes);
+    void reset();
+    double2* amps() const { return reinterpret_cast<double2*>(base_); }
+    size_t bytes() const { return total_; }
+
+private:
+    unsigned long long base_ = 0;
+    size_t total_ = 0, va_size_ = 0;
+    std::vector<std::pair<unsigned long long, size_t>> handles_;
 };
 
 }  // namespace pqb

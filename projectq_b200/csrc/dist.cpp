@@ -5,7 +5,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -242,6 +245,15 @@ Dist::Dist(int rank, int world, const void* uid, cudaStream_t stream) : rank_(ra
     free_mask_ = (uint64_t(1) << g_) - 1;
     ncclUniqueId id;
     std::memcpy(&id, uid, sizeof(id));
+    {
+        // the descriptor channel must listen before the (collective) communicator set-up returns on any rank
+        const char* e = getenv("PQB_REMAP_P2P");
+        if (e && e[0] == '1') {
+            uint64_t tag = 1469598103934665603ULL;  // FNV-1a of the NCCL id: the same on every rank of this run
+            for (size_t i = 0; i < sizeof(id); ++i) tag = (tag ^ reinterpret_cast<const unsigned char*>(&id)[i]) * 1099511628211ULL;
+            fdchan_.reset(new FdChannel(tag, rank_));
+        }
+    }
     ncclComm_t comm;
     nccl_check(nccl().CommInitRank(&comm, world_, id, rank_), "ncclCommInitRank");
     comm_ = comm;
@@ -410,6 +422,89 @@ void Dist::swap_bits(int r, int b, double2* shard, int n_local_bits, double2* st
     }
     for (int slot = 0; slot < n_slots && uint64_t(slot) < i; ++slot)
         cuda_check(cudaStreamWaitEvent(stream_, copied_[slot], 0), "wait(copied, final)");
+}
+
+void Dist::handshake(int peer) {
+    // a one-element exchange on the stream: it completes on either side only when both sides have reached it
+    ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+    ensure_buf(2);
+    nccl_check(nccl().GroupStart(), "ncclGroupStart");
+    nccl_check(nccl().Send(d_buf_, 1, ncclDouble, peer, comm, stream_), "ncclSend(handshake)");
+    nccl_check(nccl().Recv(d_buf_ + 1, 1, ncclDouble, peer, comm, stream_), "ncclRecv(handshake)");
+    nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+}
+
+bool Dist::swap_bits_p2p(int r, int b, const GrowBuffer& state, int n_local_bits, int device, const k::Ctx& ctx,
+                         uint64_t* bytes_sent) {
+    if (!fdchan_ || !state.uses_vmm()) return false;
+    const int partner = rank_ ^ (1 << r);
+    PeerLink& link = links_[partner];
+    // 1. make sure each side has the other's current shard mapped: header {layout key, chunk count}, then the sizes and
+    //    descriptors if the partner does not have this layout yet
+    const uint64_t my_key = state.layout_key();
+    std::vector<int> fds;
+    std::vector<size_t> sizes;
+    uint64_t header[2] = {my_key, 0};
+    const bool need_send = link.sent_key != my_key;
+    if (need_send) {
+        if (!state.export_chunks(fds, sizes)) {
+            // tell the partner we cannot do it (chunk count ~0ULL), both fall back together
+            header[1] = ~0ULL;
+            fdchan_->send(partner, header, sizeof(header), {});
+            uint64_t theirs[2];
+            std::vector<int> none;
+            fdchan_->recv(partner, theirs, sizeof(theirs), none, 0);
+            if (theirs[1] != ~0ULL && theirs[1] != 0) {  // drain the partner's chunk message
+                std::vector<size_t> ts(theirs[1]);
+                std::vector<int> tf;
+                fdchan_->recv(partner, ts.data(), ts.size() * sizeof(size_t), tf, ts.size());
+                for (int f : tf) ::close(f);
+            }
+            return false;
+        }
+        header[1] = fds.size();
+    }
+    fdchan_->send(partner, header, sizeof(header), {});
+    if (need_send) {
+        fdchan_->send(partner, sizes.data(), sizes.size() * sizeof(size_t), fds);
+        for (int f : fds) ::close(f);
+        link.sent_key = my_key;
+    }
+    uint64_t theirs[2];
+    std::vector<int> none;
+    fdchan_->recv(partner, theirs, sizeof(theirs), none, 0);
+    if (theirs[1] == ~0ULL) return false;  // partner cannot export: both use the NCCL path
+    uint64_t ok = 1;
+    if (theirs[1] != 0) {
+        std::vector<size_t> ts(theirs[1]);
+        std::vector<int> tf;
+        fdchan_->recv(partner, ts.data(), ts.size() * sizeof(size_t), tf, ts.size());
+        if (!link.map) link.map.reset(new PeerMapping());
+        try {
+            link.map->map(device, tf, ts);
+            link.mapped_key = theirs[0];
+        } catch (const std::exception&) {
+            ok = 0;  // e.g. no peer access between the two devices
+            link.mapped_key = 0;
+        }
+        for (int f : tf) ::close(f);
+    }
+    if (!link.map || link.mapped_key != theirs[0]) ok = 0;
+    // agree on the outcome before anything is enqueued: one side must never wait in a handshake the other skipped
+    uint64_t their_ok = 0;
+    fdchan_->send(partner, &ok, sizeof(ok), {});
+    fdchan_->recv(partner, &their_ok, sizeof(their_ok), none, 0);
+    if (!their_ok) link.sent_key = 0;        // the partner could not map my shard: resend next time
+    if (!ok || !their_ok) return false;
+    // 2. both sides idle on this shard -> swap -> both sides done
+    const uint64_t half = uint64_t(1) << (n_local_bits - 1);
+    const uint64_t my_bit = 1 - uint64_t((rank_ >> r) & 1);  // rank bit 0 trades its local-bit-1 half, and vice versa
+    const uint64_t lo = (rank_ < partner) ? 0 : half / 2, cnt = (rank_ < partner) ? half / 2 : half - half / 2;
+    handshake(partner);
+    k::peer_swap(ctx, state.amps(), link.map->amps(), lo, cnt, b, int(my_bit));
+    handshake(partner);
+    if (bytes_sent) *bytes_sent += half * sizeof(double2);
+    return true;
 }
 
 void Dist::swap_bits_multi(const std::vector<std::pair<int, int>>& swaps, double2* shard, int n_local_bits,

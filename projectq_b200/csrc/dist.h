@@ -10,10 +10,14 @@
 
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <set>
 #include <vector>
 
+#include "devmem.h"
+#include "fdpass.h"
 #include "fuser.h"
+#include "kernels.cuh"
 
 namespace pqb {
 
@@ -71,6 +75,13 @@ public:
     void swap_bits_multi(const std::vector<std::pair<int, int>>& swaps, double2* shard, int n_local_bits, double2* staging,
                          uint64_t staging_amps, uint64_t* bytes_sent);
 
+    // Peer-memory exchange (opt-in, PQB_REMAP_P2P=1): map the partner's shard into this process (VMM handles exported as
+    // file descriptors and passed over a Unix socket) and swap the two halves with one kernel.  Returns false if peer
+    // mapping is not possible (then the caller uses the NCCL path).
+    bool p2p_enabled() const { return fdchan_ != nullptr; }
+    bool swap_bits_p2p(int r, int b, const GrowBuffer& state, int n_local_bits, int device, const k::Ctx& ctx,
+                       uint64_t* bytes_sent);
+
     double allreduce_sum(double v);
     void allreduce_sum_vec(double* v, size_t n);  // host vector, in place
     unsigned long long allreduce_min_u64(unsigned long long v);
@@ -86,6 +97,14 @@ private:
     cudaEvent_t received_[2] = {nullptr, nullptr}, copied_[2] = {nullptr, nullptr}, packed_[2] = {nullptr, nullptr};
     cudaEvent_t ready_ = nullptr;
     void* comm_ = nullptr;
+    struct PeerLink {
+        std::unique_ptr<PeerMapping> map;
+        uint64_t mapped_key = 0;  // layout key of the partner buffer currently mapped
+        uint64_t sent_key = 0;    // layout key of my buffer the partner has mapped
+    };
+    std::unique_ptr<FdChannel> fdchan_;
+    std::map<int, PeerLink> links_;
+    void handshake(int peer);  // stream-ordered rendezvous with one partner
     double* d_buf_ = nullptr;  // device staging for scalar collectives
     size_t d_buf_doubles_ = 0;
     void ensure_buf(size_t n);

@@ -427,8 +427,13 @@ void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uin
             ++stats_.remaps;
         } else {
             for (auto& sw : swaps) {
-                dist_->swap_bits(sw.first, sw.second, psi(), L_, scratch2_->amps(), std::max<uint64_t>(want, 1),
-                                 &stats_.remap_bytes_sent);
+                // opt-in peer-memory exchange (one kernel over NVLink, no staging); NCCL send/recv otherwise
+                if (dist_->p2p_enabled() && L_ >= 2 &&
+                    dist_->swap_bits_p2p(sw.first, sw.second, *state_, L_, device_, ctx(), &stats_.remap_bytes_sent))
+                    ++stats_.p2p_remaps;
+                else
+                    dist_->swap_bits(sw.first, sw.second, psi(), L_, scratch2_->amps(), std::max<uint64_t>(want, 1),
+                                     &stats_.remap_bytes_sent);
                 ++stats_.remaps;
             }
         }

@@ -586,6 +586,32 @@ void swap_local_bits(const Ctx& c, double2* psi, int n_bits, int b0, int b1) {
     launched(c);
 }
 
+// Global<->local qubit exchange over peer-mapped memory: amplitude j of my outgoing half (local bit `pos` == my_bit)
+// trades places with amplitude j of the partner's outgoing half (bit `pos` == 1 - my_bit) in ONE kernel — a remote
+// 128-bit load and a remote 128-bit store per amplitude over NVLink, no staging buffer, no second copy.  Both ranks of a
+// pair run it, each on its own half of the j range, so both directions of the link carry loads and stores.
+__global__ void __launch_bounds__(256) peer_swap_kernel(double2* __restrict__ mine, double2* __restrict__ peer,
+                                                        uint64_t first, uint64_t count, int pos, uint64_t my_bit) {
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t mbit = my_bit << pos, pbit = (my_bit ^ 1) << pos;
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += step) {
+        const uint64_t idx = insert_zero_bit(first + j, pos);
+        const double2 a = mine[idx | mbit];
+        const double2 b = peer[idx | pbit];
+        mine[idx | mbit] = b;
+        peer[idx | pbit] = a;
+    }
+    __threadfence_system();
+}
+
+void peer_swap(const Ctx& c, double2* mine, double2* peer, uint64_t first, uint64_t count, int pos, int my_bit) {
+    if (count == 0) return;
+    uint64_t blocks = (count + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    peer_swap_kernel<<<unsigned(blocks), 256, 0, c.stream>>>(mine, peer, first, count, pos, uint64_t(my_bit ? 1 : 0));
+    launched(c);
+}
+
 // pack / unpack one sub-block of the shard for a global<->local qubit exchange: the sub-block is the set of amplitudes
 // whose local bits at `pos` (ascending) spell `pattern`; element j of it is shard[insert_zero_bits(j, pos) | pattern].
 // `first` is the first j of this piece, `count` its length.

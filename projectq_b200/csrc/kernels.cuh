@@ -47,6 +47,8 @@ void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices,
 
 // exchange two local index bits of the state in place (n_bits >= 2)
 void swap_local_bits(const Ctx& c, double2* psi, int n_bits, int b0, int b1);
+// exchange over peer-mapped memory: swap mine[bit pos == my_bit][j] with peer[bit pos == 1 - my_bit][j], j in [first, first+count)
+void peer_swap(const Ctx& c, double2* mine, double2* peer, uint64_t first, uint64_t count, int pos, int my_bit);
 // remap support: gather / scatter the half of the shard whose local bit `pos` equals `value` (piece [first, first+count))
 void pack_half(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, int pos, int value);
 void unpack_half(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count, int pos, int value);

@@ -282,6 +282,7 @@ public:
         d["remaps"] = s.remaps;
         d["remap_bytes_sent"] = s.remap_bytes_sent;
         d["remap_ms"] = s.remap_ms;
+        d["p2p_remaps"] = s.p2p_remaps;
         return d;
     }
     void reset_stats() { check(pqb_reset_stats(sim_)); }

@@ -290,3 +290,24 @@ def test_sharded_schedule_random_circuit(lib):
     passes = [p for kind, p in events if kind == "pass"]
     wf = rand_state(rng, n)
     assert np.max(np.abs(run_oracle(n, wf, gates * 2) - run_oracle(n, wf, passes))) < 1e-12
+
+
+def _fdpass_worker(rank, world, tag, q):
+    lib = ctypes.CDLL(os.path.join(ROOT, "projectq_b200", "libpqb200.so"))
+    q.put((rank, lib.pqb_host_fdpass_selftest(ctypes.c_uint64(tag), ctypes.c_int(rank), ctypes.c_int(world))))
+
+
+def test_descriptor_channel_between_four_processes(lib):
+    """SCM_RIGHTS plumbing used to hand VMM allocation handles to partner ranks: 4 processes, every pair swaps a pipe"""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    tag = int.from_bytes(os.urandom(7), "little")
+    procs = [ctx.Process(target=_fdpass_worker, args=(r, 4, tag, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=60) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+    assert results == {0: 0, 1: 0, 2: 0, 3: 0}

@@ -62,7 +62,7 @@ def main():
     nrm = sim.norm_squared()
     if rank == 0:
         gbs = st["remap_bytes_sent"] / max(st["remap_ms"], 1e-9) / 1e6
-        print(json.dumps({"world": world, "qubits": n, "shard_GiB": 16.0 * (1 << n_local) / 2**30, "remaps": st["remaps"],
+        print(json.dumps({"world": world, "qubits": n, "shard_GiB": 16.0 * (1 << n_local) / 2**30, "remaps": st["remaps"], "p2p_remaps": st.get("p2p_remaps"),
                           "bytes_sent_per_gpu": st["remap_bytes_sent"], "remap_ms": st["remap_ms"],
                           "GBs_per_direction": gbs, "of_nominal_900": gbs / 900.0, "of_measured_770": gbs / 770.0,
                           "norm": nrm, "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}}))
