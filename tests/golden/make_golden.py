@@ -180,8 +180,39 @@ def tfim(n=12, seed=4):
             "energies": energies, "p010": p, "bits": [int(b) for b in q], "trace": trace}
 
 
+def brickwork20(seed=6):
+    """BASELINE config 2 at a size the reference finishes in seconds: same generator as bench.py (tests/helpers.py),
+    20 qubits, depth 20, driven through the reference engine with gate_fusion=True and an empty engine list"""
+    from projectq.ops import CNOT, CZ, Rx, Ry, Rz
+
+    n, depth = 20, 20
+    trace = []
+    sim = Simulator(gate_fusion=True, rnd_seed=seed)
+    sim._simulator = Recorder(seed, trace)
+    eng = MainEngine(sim, [])
+    q = eng.allocate_qureg(n)
+    rng = np.random.default_rng(2026)
+    for d in range(depth):
+        for i in range(n):
+            kind = int(rng.integers(0, 3))
+            th = float(rng.uniform(0, 2 * np.pi))
+            (Rx, Ry, Rz)[kind](th) | q[i]
+        for i in range(d % 2, n - 1, 2):
+            if int(rng.integers(0, 2)) == 0:
+                CNOT | (q[i], q[i + 1])
+            else:
+                CZ | (q[i], q[i + 1])
+    eng.flush()
+    sample_state(sim, trace, 512, rng)
+    p = sim.get_probability("0110", q[3:7])
+    All(Measure) | q
+    eng.flush()
+    return {"config": "random brickwork circuit, 20 qubits, depth 20 (Rx/Ry/Rz + CNOT/CZ), gate_fusion=True, rnd_seed=%d" % seed,
+            "p0110": p, "bits": [int(b) for b in q], "trace": trace}
+
+
 def main():
-    for name, fn in (("qft20", qft20), ("shor4087", shor), ("tfim12", tfim)):
+    for name, fn in (("qft20", qft20), ("shor4087", shor), ("tfim12", tfim), ("brickwork20", brickwork20)):
         data = fn()
         path = os.path.join(OUT, name + ".json")
         with open(path, "w") as f:

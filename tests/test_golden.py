@@ -69,8 +69,13 @@ def test_oracle_reproduces_reference_golden(name):
 
 
 def test_oracle_reproduces_qft20_golden():
-    data = load("qft20")  # 2^20 amplitudes through NumPy gathers: ~1 min
+    data = load("qft20")  # 2^20 amplitudes through NumPy gathers
     assert replay(OracleSimulator(1), data["trace"], oracle_amplitudes) > 10
+
+
+def test_oracle_reproduces_brickwork20_golden():
+    data = load("brickwork20")  # 590 gates on 2^20 amplitudes
+    assert replay(OracleSimulator(_seed(data)), data["trace"], oracle_amplitudes) > 10
 
 
 def _seed(data):
@@ -81,7 +86,7 @@ def _seed(data):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["qft20", "shor4087", "tfim12"])
+@pytest.mark.parametrize("name", ["qft20", "shor4087", "tfim12", "brickwork20"])
 @pytest.mark.parametrize("fusion", [0, 1, 5])
 def test_cuda_engine_reproduces_reference_golden(name, fusion):
     from projectq_b200.backend import SimulatorBackend
