@@ -6,11 +6,19 @@
 // reference's Python binding turns the state into a Python list in cheat() (_cppsim.cpp:65), which is
 // unusable at >= 27 qubits; here the same C++ class is driven directly.
 //
-// usage: refsim <circuit.bin> <fusion 0|1> [samples.bin] [out.bin]
+// usage: refsim <circuit.bin> <fusion 0|1> [samples.bin out.bin [ops.bin results.bin]]
 //   circuit.bin : "PQBC" u32 version=1, u32 n_qubits, u32 n_gates, then per gate
 //                 u32 k, u32 nc, u32 targets[k], u32 ctrls[nc], f64 matrix[2*4^k] (row-major re,im)
 //   samples.bin : u64 count, u64 idx[count]   -> amplitudes written to out.bin as f64 re,im pairs
-// Prints one JSON line with timings (alloc, gates) and the thread count.
+//   ops.bin     : "PQBO" u32 version=1, u32 n_ops, then per op u32 kind + payload; executed after the gates and before
+//                 the amplitudes are sampled, every result appended to results.bin as f64:
+//                   1 time evolution : f64 t, ids, ctrl, terms                 (no result)
+//                   2 expectation    : ids, terms                              -> 1 value
+//                   3 probability    : ids, u32 bits[n_ids]                    -> 1 value
+//                   4 measure        : ids                                     -> n_ids values (0/1)
+//                   5 (x*a) mod N    : i64 a, i64 N, ids (one register), ctrl  (no result)
+//                 ids/ctrl = u32 n, u32[n]; terms = u32 n_terms, per term f64 coeff, u32 len, (u32 index, u32 'X'|'Y'|'Z')[len]
+// Prints one JSON line with timings (alloc, gates, ops) and the thread count.
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -28,6 +36,78 @@ struct GateRec {
 };
 
 static bool rd(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n; }
+
+static std::vector<unsigned> rd_ids(FILE* f) {
+    uint32_t n = 0;
+    if (!rd(f, &n, 4)) { fprintf(stderr, "truncated ops file\n"); exit(2); }
+    std::vector<unsigned> v(n);
+    if (n && !rd(f, v.data(), 4 * size_t(n))) { fprintf(stderr, "truncated ops file\n"); exit(2); }
+    return v;
+}
+
+static Simulator::TermsDict rd_terms(FILE* f) {
+    uint32_t nt = 0;
+    if (!rd(f, &nt, 4)) { fprintf(stderr, "truncated ops file\n"); exit(2); }
+    Simulator::TermsDict td(nt);
+    for (auto& t : td) {
+        uint32_t len = 0;
+        if (!rd(f, &t.second, 8) || !rd(f, &len, 4)) { fprintf(stderr, "truncated ops file\n"); exit(2); }
+        for (uint32_t i = 0; i < len; ++i) {
+            uint32_t w[2];
+            if (!rd(f, w, 8)) { fprintf(stderr, "truncated ops file\n"); exit(2); }
+            t.first.emplace_back(unsigned(w[0]), char(w[1]));
+        }
+    }
+    return td;
+}
+
+// the post-circuit script (see the header comment); results are appended to `res`
+static void run_ops(Simulator& sim, const char* path, std::vector<double>& res) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { perror("ops"); exit(2); }
+    char magic[4];
+    uint32_t ver = 0, n_ops = 0;
+    if (!rd(f, magic, 4) || memcmp(magic, "PQBO", 4) || !rd(f, &ver, 4) || !rd(f, &n_ops, 4)) {
+        fprintf(stderr, "bad ops header\n");
+        exit(2);
+    }
+    for (uint32_t o = 0; o < n_ops; ++o) {
+        uint32_t kind = 0;
+        if (!rd(f, &kind, 4)) { fprintf(stderr, "truncated ops file\n"); exit(2); }
+        if (kind == 1) {
+            double t = 0.0;
+            if (!rd(f, &t, 8)) exit(2);
+            auto ids = rd_ids(f);
+            auto ctrl = rd_ids(f);
+            auto td = rd_terms(f);
+            sim.emulate_time_evolution(td, t, ids, ctrl);
+        } else if (kind == 2) {
+            auto ids = rd_ids(f);
+            auto td = rd_terms(f);
+            res.push_back(sim.get_expectation_value(td, ids));
+        } else if (kind == 3) {
+            auto ids = rd_ids(f);
+            std::vector<uint32_t> b(ids.size());
+            if (!ids.empty() && !rd(f, b.data(), 4 * ids.size())) exit(2);
+            std::vector<bool> bits(b.begin(), b.end());
+            res.push_back(sim.get_probability(bits, ids));
+        } else if (kind == 4) {
+            auto ids = rd_ids(f);
+            for (bool b : sim.measure_qubits_return(ids)) res.push_back(b ? 1.0 : 0.0);
+        } else if (kind == 5) {
+            int64_t a = 0, N = 0;
+            if (!rd(f, &a, 8) || !rd(f, &N, 8)) exit(2);
+            auto ids = rd_ids(f);
+            auto ctrl = rd_ids(f);
+            std::vector<std::vector<unsigned>> quregs{ids};
+            sim.emulate_math_multiplyByConstantModN(int(a), int(N), quregs, ctrl);
+        } else {
+            fprintf(stderr, "unknown op kind %u\n", kind);
+            exit(2);
+        }
+    }
+    fclose(f);
+}
 
 int main(int argc, char** argv) {
     if (argc < 3) {
@@ -76,10 +156,22 @@ int main(int argc, char** argv) {
 #if defined(_OPENMP)
     threads = omp_get_max_threads();
 #endif
+    std::vector<double> results;
+    if (argc >= 7) {
+        run_ops(sim, argv[5], results);
+        sim.run();
+        FILE* o = fopen(argv[6], "wb");
+        if (!o) { perror("results"); return 2; }
+        if (!results.empty()) fwrite(results.data(), 8, results.size(), o);
+        fclose(o);
+    }
+    auto t3 = clk::now();
     double ta = std::chrono::duration<double>(t1 - t0).count();
     double tg = std::chrono::duration<double>(t2 - t1).count();
-    printf("{\"n_qubits\": %u, \"n_gates\": %u, \"fusion\": %d, \"threads\": %d, \"alloc_s\": %.6f, \"gates_s\": %.6f}\n",
-           nq, ng, int(fusion), threads, ta, tg);
+    double to = std::chrono::duration<double>(t3 - t2).count();
+    printf("{\"n_qubits\": %u, \"n_gates\": %u, \"fusion\": %d, \"threads\": %d, \"alloc_s\": %.6f, \"gates_s\": %.6f, "
+           "\"ops_s\": %.6f}\n",
+           nq, ng, int(fusion), threads, ta, tg, to);
 
     if (argc >= 5) {
         FILE* s = fopen(argv[3], "rb");

@@ -149,22 +149,34 @@ class Simulator(BasicEngine):
         elif isinstance(gate, TimeEvolution):
             terms = [(list(term), coefficient) for term, coefficient in gate.hamiltonian.terms.items()]
             self._simulator.emulate_time_evolution(terms, gate.time, _ids(cmd.qubits[0]), _ids(cmd.control_qubits))
-        elif len(gate.matrix) <= 2**_MAX_GATE_QUBITS:
-            matrix = gate.matrix
-            ids = [qb.id for qureg in cmd.qubits for qb in qureg]
-            if 2 ** len(ids) != len(matrix):
-                raise Exception(
-                    f"Simulator: Error applying {str(gate)} gate: {int(math.log(len(matrix), 2))}-qubit"
-                    f" gate applied to {len(ids)} qubits."
-                )
-            self._simulator.apply_controlled_gate(matrix.tolist(), ids, _ids(cmd.control_qubits))
-            if not self._gate_fusion:
-                self._simulator.run()
         else:
+            matrix, ids, ctrl = self._matrix_gate(cmd)
+            native = self._simulator
+            if hasattr(native, "apply_gate_list"):
+                native.apply_gate_list([(matrix, ids, ctrl)], self._gate_fusion)
+            else:  # a reference-style native object swapped in (the reference's tests do that, _simulator_test.py:80-93)
+                native.apply_controlled_gate(matrix.tolist() if hasattr(matrix, "tolist") else matrix, ids, ctrl)
+                if not self._gate_fusion:
+                    native.run()
+
+    @staticmethod
+    def _matrix_gate(cmd):
+        """(matrix, target ids, control ids) of a matrix-gate command, with the reference's checks and messages
+        (reference: _simulator.py:399-420)"""
+        gate = cmd.gate
+        matrix = gate.matrix
+        if len(matrix) > 2**_MAX_GATE_QUBITS:
             raise Exception(
                 "This simulator only supports controlled k-qubit gates with k < 6!\nPlease add an auto-replacer"
                 " engine to your list of compiler engines."
             )
+        ids = [qb.id for qureg in cmd.qubits for qb in qureg]
+        if 2 ** len(ids) != len(matrix):
+            raise Exception(
+                f"Simulator: Error applying {str(gate)} gate: {int(math.log(len(matrix), 2))}-qubit"
+                f" gate applied to {len(ids)} qubits."
+            )
+        return matrix, ids, _ids(cmd.control_qubits)
 
     def _handle_math(self, cmd):
         """Emulated arithmetic: closed-form kernels for the three constant-math gates, a lookup table built from the
@@ -184,11 +196,37 @@ class Simulator(BasicEngine):
             self._simulator.emulate_math(gate.get_math_function(cmd.qubits), quregs, ctrl)
 
     def receive(self, command_list):
-        """Simulate the commands, then pass them on if this is not the last engine (reference: _simulator.py:422-438)."""
+        """Simulate the commands, then pass them on if this is not the last engine (reference: _simulator.py:422-438).
+
+        The reference makes one native call (and one ``matrix.tolist()``) per command.  Here consecutive matrix gates of a
+        command list are handed to the native backend in ONE call (``apply_gate_list`` -> ``pqb_apply_gate_stream``), in
+        program order, before any other kind of command is handled and before this method returns, so every observable
+        (Measure, user API calls, an exception raised by a later command) sees the same simulator state as in the
+        reference."""
+        native = self._simulator
+        batched = hasattr(native, "apply_gate_list")
+        batch = []
+
+        def flush_batch():
+            if batch:
+                native.apply_gate_list(batch, self._gate_fusion)
+                del batch[:]
+
         for cmd in command_list:
-            if cmd.gate == FlushGate():
-                self._simulator.run()
+            gate = cmd.gate
+            if gate == FlushGate():
+                flush_batch()
+                native.run()
+            elif (batched and gate != Measure and gate != Allocate and gate != Deallocate
+                  and not isinstance(gate, (BasicMathGate, TimeEvolution))):
+                try:
+                    batch.append(self._matrix_gate(cmd))
+                except Exception:
+                    flush_batch()  # everything before the offending command has been applied, as in the reference
+                    raise
             else:
+                flush_batch()
                 self._handle(cmd)
             if not self.is_last_engine:
                 self.send([cmd])
+        flush_batch()

@@ -23,6 +23,9 @@ thread_local std::string g_create_error;  // message of the last failing call th
 template <class F>
 int guarded(pqb_sim* s, F&& f) {
     if (!s || !s->eng) return PQB_ERR_RUNTIME;
+    // the current device is per-thread state: make the engine's device current for this call and restore the caller's
+    // afterwards, so that engines on different devices, or calls from other threads, never launch on the wrong one
+    pqb::DeviceGuard on_device(s->eng->device());
     try {
         f(*s->eng);
         return PQB_OK;
@@ -62,6 +65,19 @@ int pqb_create(uint32_t seed, const pqb_opts* opts, pqb_sim** out) {
     pqb_opts o;
     std::memset(&o, 0, sizeof(o));
     if (opts) o = *opts;
+    // the constructor makes the engine's device current; give the caller's thread its own device back afterwards
+    struct RestoreDevice {
+        int prev = -1;
+        RestoreDevice() {
+            if (cudaGetDevice(&prev) != cudaSuccess) {
+                cudaGetLastError();
+                prev = -1;
+            }
+        }
+        ~RestoreDevice() {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    } restore_device;
     try {
         pqb_sim* s = new pqb_sim{nullptr, {}};
         try {
@@ -89,7 +105,11 @@ int pqb_create(uint32_t seed, const pqb_opts* opts, pqb_sim** out) {
 
 void pqb_destroy(pqb_sim* sim) {
     if (!sim) return;
-    delete sim->eng;
+    if (sim->eng) {
+        pqb::DeviceGuard on_device(sim->eng->device());
+        delete sim->eng;
+        sim->eng = nullptr;
+    }
     delete sim;
 }
 

@@ -101,7 +101,7 @@ void GrowBuffer::init(int device) {
     vmm_ = true;
 }
 
-void GrowBuffer::ensure(size_t bytes) {
+void GrowBuffer::ensure(size_t bytes, cudaStream_t stream) {
     if (!inited_) throw std::logic_error("GrowBuffer::ensure before init");
     if (bytes <= mapped_) return;
     if (vmm_) {
@@ -138,7 +138,14 @@ void GrowBuffer::ensure(size_t bytes) {
         throw std::bad_alloc();
     }
     if (mapped_) {
-        cudaMemcpy(fresh, reinterpret_cast<void*>(base_), mapped_, cudaMemcpyDeviceToDevice);
+        // the engine's stream is non-blocking, so a legacy-stream copy would not wait for kernels still in flight on it
+        cudaError_t e = cudaMemcpyAsync(fresh, reinterpret_cast<void*>(base_), mapped_, cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(fresh);
+            throw std::runtime_error(std::string("GrowBuffer: copy while growing failed: ") + cudaGetErrorString(e));
+        }
         cudaFree(reinterpret_cast<void*>(base_));
     }
     base_ = reinterpret_cast<unsigned long long>(fresh);

@@ -23,8 +23,10 @@ public:
     GrowBuffer& operator=(const GrowBuffer&) = delete;
 
     void init(int device);
-    // make at least `bytes` usable; existing contents are preserved; throws std::bad_alloc when the device is full
-    void ensure(size_t bytes);
+    // make at least `bytes` usable; existing contents are preserved; throws std::bad_alloc when the device is full.
+    // `stream` = the stream whose queued work may still be writing the buffer: the (non-VMM fallback) grow-by-copy is
+    // ordered after it.
+    void ensure(size_t bytes, cudaStream_t stream = nullptr);
     // give physical memory back, keeping at least `bytes` mapped
     void shrink_to(size_t bytes);
     void release() { shrink_to(0); }

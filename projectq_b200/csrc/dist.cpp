@@ -346,6 +346,11 @@ void Dist::release_rank_bit(int r, bool value, double2* shard, uint64_t n_amps) 
                 nccl_check(nccl().Recv(p, cnt, ncclDouble, partner, comm, stream_), "ncclRecv");
         }
         if (sender) cuda_check(cudaMemsetAsync(shard, 0, n_amps * sizeof(double2), stream_), "memset");
+    } else if ((rank_ >> r) & 1) {
+        // value 0: the ranks with the bit set may still hold residue below the is_classical tolerance (|psi|^2 <= 1e-12);
+        // a free rank bit must be *exactly* zero outside value 0, because the bit is handed out again as a fresh |0> qubit
+        // (the reference drops that half, simulator.hpp:123-133)
+        cuda_check(cudaMemsetAsync(shard, 0, n_amps * sizeof(double2), stream_), "memset");
     }
     free_mask_ |= uint64_t(1) << r;
 }

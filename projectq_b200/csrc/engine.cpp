@@ -25,6 +25,8 @@ namespace {
 constexpr size_t kScalarDoubles = 8192;  // device/pinned scalar scratch (bins of the measurement search live here)
 constexpr size_t kMaxPending = 4096;     // gates buffered before the fuser is drained on its own
 constexpr int kBinBits = 10;             // measurement search: logical bits resolved per level
+constexpr int kMinLocalBits = 8;         // sharded runs: qubits go to local bits until a shard holds this many, then to
+                                         // free rank bits (so the widest gate plus its eviction room always fits on-device)
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -150,7 +152,7 @@ double Engine::allreduce_sum(double v) { return dist_ ? dist_->allreduce_sum(v) 
 
 void Engine::ensure_scratch(GrowBuffer& b, size_t bytes) {
     try {
-        b.ensure(bytes);
+        b.ensure(bytes, stream_);
     } catch (const std::bad_alloc&) {
         throw CudaErr("out of device memory for a scratch copy of the state (" + std::to_string(bytes >> 20) + " MiB)");
     }
@@ -185,20 +187,22 @@ void Engine::allocate_qubit(uint32_t id) {
     if (known(id)) throw RuntimeErr("AllocateQubit: ID already exists. Qubit IDs should be unique.");
     if (n_ >= 62) throw RuntimeErr("AllocateQubit: too many qubits");
     // pending gates keep their meaning: the new qubit is a new most-significant logical bit (simulator.hpp:57)
-    if (dist_ && dist_->has_free_rank_bit()) {
-        // a free rank bit is all-zero outside value 0, which is exactly a fresh |0> qubit: no data moves
+    if (dist_ && dist_->has_free_rank_bit() && L_ >= kMinLocalBits) {
+        // a free rank bit is all-zero outside value 0, which is exactly a fresh |0> qubit: no data moves.  The first
+        // kMinLocalBits qubits take local bits instead: a lazily allocating program (allocate q0; H | q0; flush) must be
+        // able to run its first gates without a remap that has nothing to evict.
         const int r = dist_->take_free_rank_bit();
         loc_.push_back(uint8_t(64 + r));
     } else {
         const size_t old_bytes = sizeof(double2) << L_;
         try {
-            state_->ensure(old_bytes * 2);
+            state_->ensure(old_bytes * 2, stream_);
         } catch (const std::bad_alloc&) {
             // give the scratch copies back and retry once
             scratch1_->release();
             scratch2_->release();
             try {
-                state_->ensure(old_bytes * 2);
+                state_->ensure(old_bytes * 2, stream_);
             } catch (const std::bad_alloc&) {
                 throw CudaErr("AllocateQubit: out of device memory at " + std::to_string(n_ + 1) + " qubits");
             }
@@ -1119,7 +1123,7 @@ void Engine::init_random_state(uint32_t n_qubits, uint64_t seed) {
     n_ = int(n_qubits);
     int g = 0;
     if (dist_) {
-        g = std::min<int>(dist_->rank_bits(), n_);
+        g = std::min<int>(dist_->rank_bits(), std::max(0, n_ - kMinLocalBits));
         dist_->reset_rank_bits(g);
     }
     L_ = n_ - g;
@@ -1128,12 +1132,12 @@ void Engine::init_random_state(uint32_t n_qubits, uint64_t seed) {
         loc_.push_back(uint8_t(p < L_ ? p : 64 + (p - L_)));
     }
     try {
-        state_->ensure(local_amps() * sizeof(double2));
+        state_->ensure(local_amps() * sizeof(double2), stream_);
     } catch (const std::bad_alloc&) {
         scratch1_->release();
         scratch2_->release();
         try {
-            state_->ensure(local_amps() * sizeof(double2));
+            state_->ensure(local_amps() * sizeof(double2), stream_);
         } catch (const std::bad_alloc&) {
             throw CudaErr("init_random_state(): out of device memory");
         }

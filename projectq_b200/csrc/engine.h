@@ -35,6 +35,27 @@ struct CudaErr : std::runtime_error {
 
 class Dist;  // sharded-state communicator (dist.h)
 
+// RAII: make `device` the calling thread's current CUDA device, restore the previous one on scope exit
+class DeviceGuard {
+public:
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev_) != cudaSuccess) {
+            cudaGetLastError();
+            prev_ = -1;
+        }
+        if (prev_ != device) cudaSetDevice(device);
+        else prev_ = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev_ >= 0) cudaSetDevice(prev_);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+
+private:
+    int prev_ = -1;
+};
+
 struct TermsView {
     size_t n_terms;
     const size_t* offsets;
@@ -67,6 +88,7 @@ public:
     void collapse_wavefunction(const uint32_t* ids, size_t n_ids, const uint8_t* values, size_t n_values);
     void run();
     size_t num_qubits() const { return size_t(n_); }
+    int device() const { return device_; }
     size_t cheat_map(uint32_t* ids, uint32_t* pos, size_t cap);
     void cheat_state(double* out, size_t cap_amps);
 

@@ -252,6 +252,37 @@ public:
         py::gil_scoped_release nogil;
         check(pqb_apply_gate_stream(sim_, s.data(), s.size(), n_gates, fuse ? 1 : 0));
     }
+    // f1: a whole command list's worth of matrix gates in ONE native call.  gates = list of
+    // (matrix, target ids, control ids); matrices are anything NumPy can view as a complex 2^k x 2^k array, so the
+    // engine hands over `gate.matrix` as it is (the reference converts every matrix with .tolist(), _simulator.py:412).
+    void apply_gate_list(const py::list& gates, bool fuse) {
+        std::string buf;
+        buf.reserve(size_t(py::len(gates)) * 96);
+        size_t n_gates = 0;
+        auto put32 = [&buf](uint32_t v) { buf.append(reinterpret_cast<const char*>(&v), 4); };
+        for (auto item : gates) {
+            py::sequence g = py::reinterpret_borrow<py::sequence>(item);
+            if (py::len(g) != 3) throw py::type_error("each gate must be a (matrix, ids, ctrl) triple");
+            carray m = carray::ensure(g[0]);
+            if (!m) throw py::type_error("gate matrix is not convertible to a complex array");
+            const std::vector<uint32_t> ids = g[1].cast<std::vector<uint32_t>>();
+            const std::vector<uint32_t> ctrl = g[2].cast<std::vector<uint32_t>>();
+            if (ids.empty() || ids.size() > 5) throw py::value_error("Gates with more than 5 qubits are not supported!");
+            const size_t d = size_t(1) << ids.size();
+            if (m.ndim() != 2 || size_t(m.shape(0)) != d || size_t(m.shape(1)) != d)
+                throw py::value_error("apply_gate_list(): the matrix must be 2^k x 2^k for k target qubits");
+            if (ctrl.size() > 64) throw py::value_error("apply_gate_list(): more than 64 control qubits");
+            put32(uint32_t(ids.size()));
+            put32(uint32_t(ctrl.size()));
+            buf.append(reinterpret_cast<const char*>(ids.data()), 4 * ids.size());
+            buf.append(reinterpret_cast<const char*>(ctrl.data()), 4 * ctrl.size());
+            buf.append(reinterpret_cast<const char*>(m.data()), 16 * d * d);
+            ++n_gates;
+        }
+        if (n_gates == 0) return;
+        py::gil_scoped_release nogil;
+        check(pqb_apply_gate_stream(sim_, buf.data(), buf.size(), n_gates, fuse ? 1 : 0));
+    }
     void init_random_state(uint32_t n, uint64_t seed) { check(pqb_init_random_state(sim_, n, seed)); }
     double norm_squared() {
         double v = 0.0;
@@ -350,6 +381,7 @@ PYBIND11_MODULE(_pqb_shim, m) {
         .def("get_amplitudes", &Simulator::get_amplitudes)
         .def("apply_gate_stream", &Simulator::apply_gate_stream, py::arg("packed"), py::arg("n_gates"),
              py::arg("fuse") = true)
+        .def("apply_gate_list", &Simulator::apply_gate_list, py::arg("gates"), py::arg("fuse") = true)
         .def("init_random_state", &Simulator::init_random_state)
         .def("norm_squared", &Simulator::norm_squared)
         .def("synchronize", &Simulator::synchronize)

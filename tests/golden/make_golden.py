@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ from the UNMODIFIED reference (run in the build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--out DIR]
 
 The reference's Python package is imported from /root/reference and its compiled C++ simulator from oracle/_ref (built
 by oracle/Makefile).  Each fixture is the exact sequence of native-seam calls (`_cppsim.Simulator` methods,
@@ -23,13 +23,11 @@ from tests import refenv  # noqa: E402
 refenv.import_projectq()
 
 import projectq.backends._sim._cppsim as ref_cppsim  # noqa: E402
-from projectq import MainEngine  # noqa: E402
 from projectq.backends import Simulator  # noqa: E402
-from projectq.cengines import AutoReplacer, DecompositionRuleSet, InstructionFilter, LocalOptimizer, TagRemover  # noqa: E402
-from projectq.meta import Control  # noqa: E402
-from projectq.ops import QFT, All, BasicMathGate, H, Measure, QubitOperator, R, Ry, Swap, TimeEvolution, X, get_inverse  # noqa: E402
 
-OUT = os.path.dirname(os.path.abspath(__file__))
+from tests.golden import programs  # noqa: E402
+
+OUT = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.dirname(os.path.abspath(__file__))
 
 
 def enc(o):
@@ -78,142 +76,42 @@ def sample_state(sim_engine, trace, n_samples, rng):
     """record amplitudes at seeded sample indices (as a get_amplitudes-style check) + the norm"""
     mapping, vec = sim_engine._simulator._inner.cheat()
     vec = np.asarray(vec)
-    idx = sorted(int(i) for i in rng.choice(len(vec), size=min(n_samples, len(vec)), replace=False))
+    idx = programs.sample_indices(len(vec), n_samples, rng)
     trace.append({"m": "_check_amplitudes", "a": [idx], "r": [[vec[i].real, vec[i].imag] for i in idx],
                   "map": {str(k): int(v) for k, v in dict(mapping).items()}})
 
 
-def qft20():
+CONFIGS = {
+    "qft20": "QFT on 20 qubits + Measure, Simulator(gate_fusion=True, rnd_seed=1), default engine list, seeded Ry prep",
+    "shor4087": "Shor N=4087 a=7 via examples/shor.py's run_shor with emulate_math on, rnd_seed=3",
+    "tfim12": "12-qubit open-chain TFIM (J=1, h=0.7): Ry prep, 2 x [TimeEvolution(0.3, H), <H>]",
+    "brickwork20": "random brickwork circuit, 20 qubits, depth 20 (Rx/Ry/Rz + CNOT/CZ), gate_fusion=True, rnd_seed=6",
+}
+
+
+def record(name):
+    """run one program of tests/golden/programs.py on the reference engine + reference C++ simulator, recording the seam"""
     trace = []
-    sim = Simulator(gate_fusion=True, rnd_seed=1)
-    sim._simulator = Recorder(1, trace)
-    eng = MainEngine(sim)  # default engine list
-    q = eng.allocate_qureg(20)
-    rng = np.random.default_rng(20)
-    for i in range(20):  # seeded product-state preparation so that the QFT output has structure
-        Ry(float(rng.uniform(0, np.pi))) | q[i]
-    QFT | q
-    eng.flush()
-    sample_state(sim, trace, 256, rng)
-    All(Measure) | q
-    eng.flush()
-    bits = [int(b) for b in q]
-    return {"config": "QFT on 20 qubits + Measure, Simulator(gate_fusion=True, rnd_seed=1), default engine list, seeded Ry prep",
-            "measured_bits": bits, "trace": trace}
 
+    def make_sim(gate_fusion, rnd_seed):
+        sim = Simulator(gate_fusion=gate_fusion, rnd_seed=rnd_seed)
+        sim._simulator = Recorder(rnd_seed, trace)
+        return sim
 
-def shor(N=4087, a=7, seed=3):
-    """examples/shor.py run_shor with emulation on (the InstructionFilter lets BasicMathGate through)"""
-    import projectq.libs.math
-    import projectq.setups.decompositions
-    from projectq.libs.math import AddConstant, AddConstantModN, MultiplyByConstantModN
-
-    trace = []
-    sim = Simulator(gate_fusion=True, rnd_seed=seed)
-    sim._simulator = Recorder(seed, trace)
-
-    def high_level_gates(eng, cmd):
-        g = cmd.gate
-        if g == QFT or get_inverse(g) == QFT or g == Swap:
-            return True
-        if isinstance(g, BasicMathGate):
-            return isinstance(g, (AddConstant, AddConstantModN, MultiplyByConstantModN))
-        return eng.next_engine.is_available(cmd)
-
-    rule_set = DecompositionRuleSet(modules=[projectq.libs.math, projectq.setups.decompositions])
-    engines = [AutoReplacer(rule_set), InstructionFilter(high_level_gates), TagRemover(), LocalOptimizer(3),
-               AutoReplacer(rule_set), TagRemover(), LocalOptimizer(3)]
-    eng = MainEngine(sim, engines)
-    # body of run_shor (examples/shor.py:31-86), restated
-    n = int(np.ceil(np.log2(N)))
-    x = eng.allocate_qureg(n)
-    X | x[0]
-    measurements = [0] * (2 * n)
-    ctrl_qubit = eng.allocate_qubit()
-    for k in range(2 * n):
-        current_a = pow(a, 1 << (2 * n - 1 - k), N)
-        H | ctrl_qubit
-        with Control(eng, ctrl_qubit):
-            MultiplyByConstantModN(current_a, N) | x
-        for i in range(k):
-            if measurements[i]:
-                R(-np.pi / (1 << (k - i))) | ctrl_qubit
-        H | ctrl_qubit
-        Measure | ctrl_qubit
-        eng.flush()
-        measurements[k] = int(ctrl_qubit)
-        if measurements[k]:
-            X | ctrl_qubit
-    All(Measure) | x
-    eng.flush()
-    xbits = [int(b) for b in x]
-    return {"config": "Shor N=%d a=%d via examples/shor.py's run_shor with emulate_math on, rnd_seed=%d" % (N, a, seed),
-            "measurements": measurements, "x_bits": xbits, "trace": trace}
-
-
-def tfim(n=12, seed=4):
-    trace = []
-    sim = Simulator(gate_fusion=True, rnd_seed=seed)
-    sim._simulator = Recorder(seed, trace)
-    eng = MainEngine(sim, [])
-    q = eng.allocate_qureg(n)
-    rng = np.random.default_rng(seed)
-    for i in range(n):
-        Ry(float(rng.uniform(0, np.pi))) | q[i]
-    Hop = QubitOperator(())
-    Hop *= 0.0
-    for i in range(n - 1):
-        Hop += QubitOperator("Z%d Z%d" % (i, i + 1), -1.0)
-    for i in range(n):
-        Hop += QubitOperator("X%d" % i, -0.7)
-    eng.flush()
-    energies = [sim.get_expectation_value(Hop, q)]
-    for it in range(2):
-        TimeEvolution(0.3, Hop) | q
-        eng.flush()
-        energies.append(sim.get_expectation_value(Hop, q))
-    sample_state(sim, trace, 256, rng)
-    p = sim.get_probability("010", q[:3])
-    All(Measure) | q
-    eng.flush()
-    return {"config": "%d-qubit open-chain TFIM (J=1, h=0.7): Ry prep, 2 x [TimeEvolution(0.3, H), <H>]" % n,
-            "energies": energies, "p010": p, "bits": [int(b) for b in q], "trace": trace}
-
-
-def brickwork20(seed=6):
-    """BASELINE config 2 at a size the reference finishes in seconds: same generator as bench.py (tests/helpers.py),
-    20 qubits, depth 20, driven through the reference engine with gate_fusion=True and an empty engine list"""
-    from projectq.ops import CNOT, CZ, Rx, Ry, Rz
-
-    n, depth = 20, 20
-    trace = []
-    sim = Simulator(gate_fusion=True, rnd_seed=seed)
-    sim._simulator = Recorder(seed, trace)
-    eng = MainEngine(sim, [])
-    q = eng.allocate_qureg(n)
-    rng = np.random.default_rng(2026)
-    for d in range(depth):
-        for i in range(n):
-            kind = int(rng.integers(0, 3))
-            th = float(rng.uniform(0, 2 * np.pi))
-            (Rx, Ry, Rz)[kind](th) | q[i]
-        for i in range(d % 2, n - 1, 2):
-            if int(rng.integers(0, 2)) == 0:
-                CNOT | (q[i], q[i + 1])
-            else:
-                CZ | (q[i], q[i + 1])
-    eng.flush()
-    sample_state(sim, trace, 512, rng)
-    p = sim.get_probability("0110", q[3:7])
-    All(Measure) | q
-    eng.flush()
-    return {"config": "random brickwork circuit, 20 qubits, depth 20 (Rx/Ry/Rz + CNOT/CZ), gate_fusion=True, rnd_seed=%d" % seed,
-            "p0110": p, "bits": [int(b) for b in q], "trace": trace}
+    out = {"config": CONFIGS[name]}
+    for step in programs.PROGRAMS[name](make_sim):
+        if step[0] == "state":
+            _, sim, _, rng = step
+            sample_state(sim, trace, programs.SAMPLES[name], rng)
+        else:
+            out.update(step[1])
+    out["trace"] = trace
+    return out
 
 
 def main():
-    for name, fn in (("qft20", qft20), ("shor4087", shor), ("tfim12", tfim), ("brickwork20", brickwork20)):
-        data = fn()
+    for name in programs.PROGRAMS:
+        data = record(name)
         path = os.path.join(OUT, name + ".json")
         with open(path, "w") as f:
             json.dump(data, f, separators=(",", ":"))

@@ -1,7 +1,9 @@
-"""Makes the reference's *Python* package importable in this container (test infrastructure only).
+"""Makes the reference's *Python* package importable (test infrastructure only).
 
-/root/reference is read-only and exists only here, never on the GPU box, so everything that uses this module is a
-``not gpu`` test or a golden-vector generator.  ``import projectq`` pulls matplotlib (absent here) through
+/root/reference is read-only and exists only in the build container; oracle/Makefile stages a copy of the package under
+the git-ignored oracle/_ref/refpkg/, which travels to the GPU box with the other built artefacts, so the drop-in tests
+(`MainEngine(projectq_b200.Simulator(...))`, the reference's own test-suite on the CUDA backend) can run there.
+``import projectq`` pulls matplotlib (absent here) through
 backends/_circuits/_plot.py, and ``projectq.backends._sim._simulator`` wants the compiled ``_cppsim``; both are
 satisfied with in-memory stand-ins: a stub matplotlib, and the reference extension built by oracle/Makefile."""
 import importlib.util
@@ -9,8 +11,10 @@ import os
 import sys
 import types
 
-REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+if not os.path.isdir(os.path.join(REF, "projectq")):
+    REF = os.path.join(ROOT, "oracle", "_ref", "refpkg")
 
 
 def available():
@@ -31,8 +35,20 @@ def _stub_matplotlib():
     sys.modules["matplotlib"] = mpl
 
 
-def import_projectq():
-    """import the reference package from /root/reference with the compiled reference _cppsim attached"""
+def cuda_native_module():
+    """a stand-in for the reference's `_cppsim` extension module whose `Simulator` is the CUDA backend — the one-line
+    rebinding of INTEGRATION.md (`from projectq_b200.backend import SimulatorBackend as Simulator`)"""
+    from projectq_b200.backend import SimulatorBackend
+
+    mod = types.ModuleType("projectq.backends._sim._cppsim")
+    mod.Simulator = SimulatorBackend
+    mod.__doc__ = "projectq_b200 CUDA backend bound in place of the reference's _cppsim"
+    return mod
+
+
+def import_projectq(native="reference"):
+    """import the reference package with a native simulator module attached as projectq.backends._sim._cppsim:
+    native="reference" -> the compiled reference extension (oracle/_ref/_cppsim*.so); native="cuda" -> the CUDA backend"""
     if not available():
         return None
     _stub_matplotlib()
@@ -40,15 +56,20 @@ def import_projectq():
         sys.path.insert(0, REF)
     import glob
 
-    hits = glob.glob(os.path.join(ROOT, "oracle", "_ref", "_cppsim*.so"))
-    if hits and "projectq.backends._sim._cppsim" not in sys.modules:
-        spec = importlib.util.spec_from_file_location("projectq.backends._sim._cppsim", hits[0])
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        sys.modules["projectq.backends._sim._cppsim"] = mod
+    name = "projectq.backends._sim._cppsim"
+    if native == "cuda":
+        if name not in sys.modules or getattr(sys.modules[name], "__file__", None):
+            sys.modules[name] = cuda_native_module()
+    else:
+        hits = glob.glob(os.path.join(ROOT, "oracle", "_ref", "_cppsim*.so"))
+        if hits and name not in sys.modules:
+            spec = importlib.util.spec_from_file_location(name, hits[0])
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            sys.modules[name] = mod
     import projectq
     import projectq.backends._sim as _sim_pkg
 
-    if "projectq.backends._sim._cppsim" in sys.modules:
-        _sim_pkg._cppsim = sys.modules["projectq.backends._sim._cppsim"]
+    if name in sys.modules:
+        _sim_pkg._cppsim = sys.modules[name]
     return projectq
