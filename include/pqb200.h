@@ -68,12 +68,17 @@ typedef struct pqb_stats {
     uint64_t kernel_launches;     /* kernels of this library launched so far */
     uint64_t dense_passes[6];     /* [k] = fused dense passes applied with k target qubits (k = 1..5) */
     uint64_t gates_ingested;      /* apply_controlled_gate calls */
-    uint64_t remaps;              /* global<->local qubit remaps (sharded state) */
+    uint64_t remaps;              /* global<->local qubit remaps (sharded state); one remap may move several qubits */
     uint64_t remap_bytes_sent;    /* bytes this rank sent over NVLink in remaps */
-    double remap_ms;              /* device time spent in remaps */
+    double remap_ms;              /* device time the main stream spent waiting for remaps (the exposed part) */
     uint64_t diag_passes;         /* passes applied by the diagonal kernel */
-    uint64_t p2p_remaps;          /* remaps done by the peer-memory exchange kernel (opt-in) rather than NCCL send/recv */
-    uint64_t reserved_[6];
+    uint64_t p2p_remaps;          /* remaps done by the peer-memory exchange kernel rather than NCCL send/recv */
+    uint64_t pipelined_remaps;    /* of those: remaps executed slice by slice, overlapped with the passes around them */
+    uint64_t remap_qubits;        /* qubits moved between rank bits and local bits */
+    double remap_comm_ms;         /* device time of the exchange kernels on the communication stream */
+    double pass_ms[6];            /* profiling on: summed device time of the dense launches with k targets */
+    double diag_ms;               /* profiling on: summed device time of the diagonal launches */
+    uint64_t reserved_[4];
 } pqb_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------ */
@@ -156,13 +161,28 @@ PQB_API int pqb_synchronize(pqb_sim* sim);
 /* CUDA-event stopwatch on the engine's stream: start, ... enqueue work ..., stop -> elapsed device ms */
 PQB_API int pqb_timer_start(pqb_sim* sim);
 PQB_API int pqb_timer_stop(pqb_sim* sim, double* out_ms);
+/* synchronises the engine's streams and returns the counters */
 PQB_API int pqb_get_stats(pqb_sim* sim, pqb_stats* out);
+/* on: every dense / diagonal launch is bracketed by CUDA events on the engine's stream and its duration is added to
+ * pqb_stats.pass_ms[k] / diag_ms (what bench.py reports as the dominant kernel's own launch time) */
+PQB_API int pqb_set_profiling(pqb_sim* sim, int on);
 PQB_API int pqb_reset_stats(pqb_sim* sim);
 /* overwrite >= `bytes` of a scratch device buffer (L2 flush between timed iterations) */
 PQB_API int pqb_flush_l2(pqb_sim* sim, size_t bytes);
 /* micro-benchmark hook: apply one dense k-qubit gate pass directly at the given *bit positions* (bypasses the fuser) */
 PQB_API int pqb_bench_dense_pass(pqb_sim* sim, const double* matrix_re_im, const uint32_t* positions, size_t k,
                                  uint64_t ctrl_mask, int repeats, double* out_ms_per_pass);
+/* self-test hook: apply one dense pass slice by slice — the launch is restricted in turn to every value of the local bits in
+ * slice_mask (none of which may be a target or control) — which must equal one unrestricted pass; this is how the sharded
+ * engine runs the passes around a remap while other slices are on the wire */
+PQB_API int pqb_selftest_sliced_pass(pqb_sim* sim, const double* matrix_re_im, const uint32_t* positions, size_t k,
+                                     uint64_t ctrl_mask, uint64_t slice_mask);
+/* self-test hook of the peer-memory exchange kernel on ONE device: `world` shards of 2^n_local_bits amplitudes live in one
+ * process, every "rank" runs its exchange kernel for the (rank bit, local bit) pairs (one kernel per slice of slice_mask),
+ * and the result is compared with the permutation a global<->local remap must perform.  out_mismatches = amplitudes in the
+ * wrong place. */
+PQB_API int pqb_selftest_exchange(int device, int world, int n_local_bits, const int32_t* pairs, size_t n_pairs,
+                                  uint64_t slice_mask, uint64_t* out_mismatches);
 /* measured FP64 FMA peak of the device in TFLOP/s (register-resident DFMA loop; roofline denominator for k = 5) */
 PQB_API int pqb_measure_fp64_peak(pqb_sim* sim, double* out_tflops);
 /* measured device-to-device copy bandwidth in GB/s (read + write bytes; cross-check of MEASURED_PEAKS.json) */

@@ -16,6 +16,7 @@ except ImportError as exc:  # no silent fallback: the reference would drop to _p
 SimulatorBackend = _pqb_shim.Simulator
 nccl_unique_id = _pqb_shim.nccl_unique_id
 version = _pqb_shim.version
+selftest_exchange = _pqb_shim.selftest_exchange
 
 
 def load_c_abi():

@@ -1,4 +1,5 @@
 // extern "C" surface of the engine (include/pqb200.h): exceptions -> status codes, nothing else.
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -9,6 +10,8 @@
 #include "dist.h"
 #include "engine.h"
 #include "fdpass.h"
+#include "bits.h"
+#include "kernels.cuh"
 
 using pqb::Engine;
 
@@ -221,6 +224,9 @@ int pqb_timer_stop(pqb_sim* s, double* out_ms) {
 int pqb_get_stats(pqb_sim* s, pqb_stats* out) {
     return guarded(s, [&](Engine& e) { e.get_stats(out); });
 }
+int pqb_set_profiling(pqb_sim* s, int on) {
+    return guarded(s, [&](Engine& e) { e.set_profiling(on != 0); });
+}
 int pqb_reset_stats(pqb_sim* s) {
     return guarded(s, [&](Engine& e) { e.reset_stats(); });
 }
@@ -231,6 +237,102 @@ int pqb_bench_dense_pass(pqb_sim* s, const double* m, const uint32_t* positions,
                          int repeats, double* out_ms) {
     return guarded(s, [&](Engine& e) { *out_ms = e.bench_dense_pass(m, positions, k, ctrl_mask, repeats); });
 }
+int pqb_selftest_sliced_pass(pqb_sim* s, const double* m, const uint32_t* positions, size_t k, uint64_t ctrl_mask,
+                             uint64_t slice_mask) {
+    return guarded(s, [&](Engine& e) { e.selftest_sliced_pass(m, positions, k, ctrl_mask, slice_mask); });
+}
+
+int pqb_selftest_exchange(int device, int world, int n_local_bits, const int32_t* pairs, size_t n_pairs, uint64_t slice_mask,
+                          uint64_t* out_mismatches) {
+    using pqb::k::ExchangeArgs;
+    if (!out_mismatches || !pairs || n_pairs == 0 || n_pairs > 3 || world < 2 || (world & (world - 1)) || n_local_bits < 1 ||
+        n_local_bits > 24)
+        return PQB_ERR_VALUE;
+    pqb::DeviceGuard on_device(device);
+    std::vector<double2*> shard(world, nullptr);
+    cudaStream_t stream = nullptr;
+    int status = PQB_OK;
+    try {
+        const uint64_t n = uint64_t(1) << n_local_bits;
+        int sm_count = 148;
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+        if (cudaStreamCreate(&stream) != cudaSuccess) throw std::runtime_error("cudaStreamCreate failed");
+        std::vector<double2> host(n);
+        for (int r = 0; r < world; ++r) {
+            if (cudaMalloc(&shard[r], n * sizeof(double2)) != cudaSuccess) throw std::runtime_error("cudaMalloc failed");
+            for (uint64_t i = 0; i < n; ++i) host[i] = make_double2(double((uint64_t(r) << n_local_bits) | i), double(r));
+            cudaMemcpy(shard[r], host.data(), n * sizeof(double2), cudaMemcpyHostToDevice);
+        }
+        std::vector<std::pair<int, int>> swaps;
+        std::vector<uint8_t> ex_bits, slice_bits;
+        for (size_t i = 0; i < n_pairs; ++i) {
+            swaps.emplace_back(pairs[2 * i], pairs[2 * i + 1]);
+            ex_bits.push_back(uint8_t(pairs[2 * i + 1]));
+        }
+        std::sort(ex_bits.begin(), ex_bits.end());
+        for (int b = 0; b < n_local_bits; ++b)
+            if ((slice_mask >> b) & 1) slice_bits.push_back(uint8_t(b));
+        if (ex_bits.size() + slice_bits.size() > 16) throw std::runtime_error("too many exchanged + slice bits");
+        const int n_slices = 1 << slice_bits.size();
+        for (int sl = 0; sl < n_slices; ++sl) {
+            const uint64_t sval = pqb::deposit_bits(uint64_t(sl), slice_bits.data(), int(slice_bits.size()));
+            for (int r = 0; r < world; ++r) {
+                const std::vector<pqb::ExchangePeer> peers = pqb::plan_exchange(r, swaps);
+                ExchangeArgs a;
+                std::memset(&a, 0, sizeof(a));
+                a.mine = shard[r];
+                a.n_peers = int(peers.size());
+                size_t e = 0, f = 0;
+                int np = 0;
+                while ((e < ex_bits.size() || f < slice_bits.size()) && np < 16) {
+                    if (f >= slice_bits.size() || (e < ex_bits.size() && ex_bits[e] < slice_bits[f]))
+                        a.pos[np++] = ex_bits[e++];
+                    else
+                        a.pos[np++] = slice_bits[f++];
+                }
+                a.n_pos = np;
+                a.count = uint64_t(1) << (n_local_bits - np);
+                uint64_t in_pattern = 0;
+                for (auto& sw : swaps) in_pattern |= uint64_t((r >> sw.first) & 1) << sw.second;
+                a.in_pattern = in_pattern | sval;
+                for (int p = 0; p < a.n_peers; ++p) {
+                    a.peer[p] = shard[peers[p].peer];
+                    a.out_pattern[p] = peers[p].pattern | sval;
+                    a.lower[p] = r < peers[p].peer ? 1 : 0;
+                }
+                a.sync = 0;  // one process, one stream: the kernels of the "ranks" simply run one after the other
+                pqb::k::peer_exchange(stream, a, sm_count);
+            }
+        }
+        if (cudaStreamSynchronize(stream) != cudaSuccess) throw std::runtime_error("exchange kernel failed");
+        // where must every amplitude be now?  old (rank, idx) -> rank bit r_i and local bit b_i trade values
+        uint64_t bad = 0;
+        for (int r = 0; r < world; ++r) {
+            cudaMemcpy(host.data(), shard[r], n * sizeof(double2), cudaMemcpyDeviceToHost);
+            for (uint64_t i = 0; i < n; ++i) {
+                int old_r = r;
+                uint64_t old_i = i;
+                for (auto& sw : swaps) {
+                    const int rb = (r >> sw.first) & 1;
+                    const int lb = int((i >> sw.second) & 1);
+                    old_r = (old_r & ~(1 << sw.first)) | (lb << sw.first);
+                    old_i = (old_i & ~(uint64_t(1) << sw.second)) | (uint64_t(rb) << sw.second);
+                }
+                const double want = double((uint64_t(old_r) << n_local_bits) | old_i);
+                if (host[i].x != want || host[i].y != double(old_r)) ++bad;
+            }
+        }
+        *out_mismatches = bad;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        status = PQB_ERR_CUDA;
+    }
+    for (auto p : shard)
+        if (p) cudaFree(p);
+    if (stream) cudaStreamDestroy(stream);
+    return status;
+}
+
 int pqb_measure_fp64_peak(pqb_sim* s, double* out) {
     return guarded(s, [&](Engine& e) { *out = e.measure_fp64_peak(); });
 }
@@ -417,7 +519,7 @@ int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, 
 int pqb_host_fdpass_selftest(uint64_t run_tag, int rank, int world) {
     // every rank hands every other rank the read end of a pipe that holds (rank * 1000 + peer) and checks what it gets
     try {
-        pqb::FdChannel ch(run_tag, rank);
+        pqb::FdChannel ch(run_tag, rank, world);
         for (int k = 1; k < world; ++k) {
             const int peer = rank ^ k;
             if (peer >= world) continue;

@@ -59,17 +59,13 @@ const DriverApi& driver() {
     return api;
 }
 
-CUmemAllocationProp alloc_prop(int device) {
+CUmemAllocationProp alloc_prop(int device, bool exportable) {
     CUmemAllocationProp prop = {};
     prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
     prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     prop.location.id = device;
-    // exportable chunks (so that a partner rank can map the shard) only when the peer-memory remap path is switched on:
-    // the default allocation path stays exactly the one the round-1 measurements were taken with
-    static const bool exportable = [] {
-        const char* e = getenv("PQB_REMAP_P2P");
-        return e && e[0] == '1';
-    }();
+    // exportable chunks (POSIX file descriptors) only for the shards of a multi-GPU run, where a partner rank maps them
+    // for the peer-memory remap; a single-GPU engine allocates exactly as before
     if (exportable) prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
     return prop;
 }
@@ -78,13 +74,14 @@ size_t round_up(size_t x, size_t g) { return (x + g - 1) / g * g; }
 
 }  // namespace
 
-void GrowBuffer::init(int device) {
+void GrowBuffer::init(int device, bool exportable) {
     if (inited_) return;
     device_ = device;
+    exportable_ = exportable;
     inited_ = true;
     const DriverApi& d = driver();
     if (!d.ok) return;  // plain cudaMalloc mode
-    CUmemAllocationProp prop = alloc_prop(device_);
+    CUmemAllocationProp prop = alloc_prop(device_, exportable_);
     size_t gran = 0;
     if (d.memGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return;
     size_t free_b = 0, total_b = 0;
@@ -108,7 +105,7 @@ void GrowBuffer::ensure(size_t bytes, cudaStream_t stream) {
         const DriverApi& d = driver();
         if (bytes > va_size_) throw std::bad_alloc();
         const size_t add = round_up(bytes - mapped_, gran_);
-        CUmemAllocationProp prop = alloc_prop(device_);
+        CUmemAllocationProp prop = alloc_prop(device_, exportable_);
         CUmemGenericAllocationHandle h = 0;
         if (d.memCreate(&h, add, &prop, 0) != CUDA_SUCCESS) {
             prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_NONE;  // not exportable here: still usable locally
@@ -129,6 +126,7 @@ void GrowBuffer::ensure(size_t bytes, cudaStream_t stream) {
         }
         chunks_.push_back({h, add});
         mapped_ += add;
+        ++generation_;
         return;
     }
     // cudaMalloc mode: allocate, copy, free
@@ -161,6 +159,7 @@ void GrowBuffer::shrink_to(size_t bytes) {
             const Chunk ch = chunks_.back();
             chunks_.pop_back();
             mapped_ -= ch.size;
+            ++generation_;
             d.memUnmap(base_ + mapped_, ch.size);
             d.memRelease(ch.handle);
         }

@@ -22,7 +22,7 @@ public:
     GrowBuffer(const GrowBuffer&) = delete;
     GrowBuffer& operator=(const GrowBuffer&) = delete;
 
-    void init(int device);
+    void init(int device, bool exportable = false);
     // make at least `bytes` usable; existing contents are preserved; throws std::bad_alloc when the device is full.
     // `stream` = the stream whose queued work may still be writing the buffer: the (non-VMM fallback) grow-by-copy is
     // ordered after it.
@@ -34,8 +34,8 @@ public:
     // Export every mapped chunk as a POSIX file descriptor (caller closes them) so that a partner process can map the
     // buffer (PeerMapping).  Returns false when the buffer is not a VMM allocation or the driver refuses.
     bool export_chunks(std::vector<int>& fds, std::vector<size_t>& sizes) const;
-    // changes whenever the address range or the set of chunks changes (a partner's mapping is then stale)
-    uint64_t layout_key() const { return base_ * 1315423911ULL + mapped_ * 2654435761ULL + chunks_.size(); }
+    // changes whenever the set of chunks changes (a partner's mapping is then stale); never repeats within a process
+    uint64_t layout_key() const { return (base_ >> 12) * 0x9E3779B97F4A7C15ULL + generation_ + 1; }
 
     void* ptr() const { return reinterpret_cast<void*>(base_); }
     double2* amps() const { return reinterpret_cast<double2*>(base_); }
@@ -49,11 +49,13 @@ private:
     };
     int device_ = 0;
     bool vmm_ = false;
+    bool exportable_ = false;
     bool inited_ = false;
     unsigned long long base_ = 0;  // CUdeviceptr
     size_t va_size_ = 0;
     size_t mapped_ = 0;
     size_t gran_ = 0;
+    uint64_t generation_ = 0;  // bumped by every change of the chunk list
     std::vector<Chunk> chunks_;
 };
 

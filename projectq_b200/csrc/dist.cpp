@@ -239,19 +239,26 @@ void Dist::get_unique_id(void* out128) {
     std::memcpy(out128, &id, sizeof(id));
 }
 
-Dist::Dist(int rank, int world, const void* uid, cudaStream_t stream) : rank_(rank), world_(world), stream_(stream) {
+Dist::Dist(int rank, int world, const void* uid, cudaStream_t stream, int device)
+    : rank_(rank), world_(world), stream_(stream), device_(device) {
     g_ = 0;
     while ((1 << g_) < world_) ++g_;
     free_mask_ = (uint64_t(1) << g_) - 1;
     ncclUniqueId id;
     std::memcpy(&id, uid, sizeof(id));
+    bool want_p2p = true;
     {
-        // the descriptor channel must listen before the (collective) communicator set-up returns on any rank
         const char* e = getenv("PQB_REMAP_P2P");
-        if (e && e[0] == '1') {
-            uint64_t tag = 1469598103934665603ULL;  // FNV-1a of the NCCL id: the same on every rank of this run
-            for (size_t i = 0; i < sizeof(id); ++i) tag = (tag ^ reinterpret_cast<const unsigned char*>(&id)[i]) * 1099511628211ULL;
-            fdchan_.reset(new FdChannel(tag, rank_));
+        if (e && e[0] == '0') want_p2p = false;
+    }
+    if (want_p2p) {
+        // the descriptor channel must listen before the (collective) communicator set-up returns on any rank
+        uint64_t tag = 1469598103934665603ULL;  // FNV-1a of the NCCL id: the same on every rank of this run
+        for (size_t i = 0; i < sizeof(id); ++i) tag = (tag ^ reinterpret_cast<const unsigned char*>(&id)[i]) * 1099511628211ULL;
+        try {
+            fdchan_.reset(new FdChannel(tag, rank_, world_));
+        } catch (const std::exception&) {
+            fdchan_.reset();  // every rank learns about it in setup_p2p's all-reduce
         }
     }
     ncclComm_t comm;
@@ -259,16 +266,28 @@ Dist::Dist(int rank, int world, const void* uid, cudaStream_t stream) : rank_(ra
     comm_ = comm;
     ensure_buf(4096);
     cuda_check(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+    {
+        int least = 0, greatest = 0;
+        cuda_check(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange");
+        cuda_check(cudaStreamCreateWithPriority(&comm_stream_, cudaStreamNonBlocking, greatest), "cudaStreamCreate(comm)");
+    }
     for (int i = 0; i < 2; ++i) {
         cuda_check(cudaEventCreateWithFlags(&received_[i], cudaEventDisableTiming), "cudaEventCreate");
         cuda_check(cudaEventCreateWithFlags(&copied_[i], cudaEventDisableTiming), "cudaEventCreate");
         cuda_check(cudaEventCreateWithFlags(&packed_[i], cudaEventDisableTiming), "cudaEventCreate");
     }
     cuda_check(cudaEventCreateWithFlags(&ready_, cudaEventDisableTiming), "cudaEventCreate");
+    if (want_p2p) setup_p2p();
 }
 
 Dist::~Dist() {
     if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+    if (comm_stream_) cudaStreamSynchronize(comm_stream_);
+    links_.clear();  // unmap the peers' buffers before our own go away
+    sync_page_.release();
+    if (h_error_) cudaFreeHost(h_error_);
+    if (d_block_counter_) cudaFree(d_block_counter_);
+    if (comm_stream_) cudaStreamDestroy(comm_stream_);
     if (comm_) nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
     if (d_buf_) cudaFree(d_buf_);
     for (int i = 0; i < 2; ++i) {
@@ -439,77 +458,221 @@ void Dist::handshake(int peer) {
     nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
 }
 
-bool Dist::swap_bits_p2p(int r, int b, const GrowBuffer& state, int n_local_bits, int device, const k::Ctx& ctx,
-                         uint64_t* bytes_sent) {
-    if (!fdchan_ || !state.uses_vmm()) return false;
-    const int partner = rank_ ^ (1 << r);
-    PeerLink& link = links_[partner];
-    // 1. make sure each side has the other's current shard mapped: header {layout key, chunk count}, then the sizes and
-    //    descriptors if the partner does not have this layout yet
-    const uint64_t my_key = state.layout_key();
+// ---------------------------------------------------------------------------------------------------------------
+// peer-memory exchange
+// ---------------------------------------------------------------------------------------------------------------
+PeerMapping* Dist::PeerLink::find(uint64_t key) {
+    for (auto& kv : maps)
+        if (kv.first == key) return kv.second.get();
+    return nullptr;
+}
+
+// chunk list of a buffer to one partner: {n_chunks or ~0}, sizes, then the descriptors (at most 32 per message)
+void Dist::send_chunks(int partner, const GrowBuffer& buf) {
     std::vector<int> fds;
     std::vector<size_t> sizes;
-    uint64_t header[2] = {my_key, 0};
-    const bool need_send = link.sent_key != my_key;
-    if (need_send) {
-        if (!state.export_chunks(fds, sizes)) {
-            // tell the partner we cannot do it (chunk count ~0ULL), both fall back together
-            header[1] = ~0ULL;
-            fdchan_->send(partner, header, sizeof(header), {});
-            uint64_t theirs[2];
-            std::vector<int> none;
-            fdchan_->recv(partner, theirs, sizeof(theirs), none, 0);
-            if (theirs[1] != ~0ULL && theirs[1] != 0) {  // drain the partner's chunk message
-                std::vector<size_t> ts(theirs[1]);
-                std::vector<int> tf;
-                fdchan_->recv(partner, ts.data(), ts.size() * sizeof(size_t), tf, ts.size());
-                for (int f : tf) ::close(f);
-            }
-            return false;
-        }
-        header[1] = fds.size();
+    uint64_t n = ~0ULL;
+    if (buf.export_chunks(fds, sizes)) n = fds.size();
+    fdchan_->send(partner, &n, sizeof(n), {});
+    if (n == ~0ULL) return;
+    if (n) fdchan_->send(partner, sizes.data(), sizes.size() * sizeof(size_t), {});
+    for (size_t off = 0; off < fds.size(); off += 32) {
+        const size_t cnt = std::min<size_t>(32, fds.size() - off);
+        const uint64_t tag = off;
+        fdchan_->send(partner, &tag, sizeof(tag), std::vector<int>(fds.begin() + off, fds.begin() + off + cnt));
     }
-    fdchan_->send(partner, header, sizeof(header), {});
-    if (need_send) {
-        fdchan_->send(partner, sizes.data(), sizes.size() * sizeof(size_t), fds);
-        for (int f : fds) ::close(f);
-        link.sent_key = my_key;
-    }
-    uint64_t theirs[2];
+    for (int f : fds) ::close(f);
+}
+
+bool Dist::recv_chunks(int partner, PeerMapping& into) {
     std::vector<int> none;
-    fdchan_->recv(partner, theirs, sizeof(theirs), none, 0);
-    if (theirs[1] == ~0ULL) return false;  // partner cannot export: both use the NCCL path
-    uint64_t ok = 1;
-    if (theirs[1] != 0) {
-        std::vector<size_t> ts(theirs[1]);
-        std::vector<int> tf;
-        fdchan_->recv(partner, ts.data(), ts.size() * sizeof(size_t), tf, ts.size());
-        if (!link.map) link.map.reset(new PeerMapping());
-        try {
-            link.map->map(device, tf, ts);
-            link.mapped_key = theirs[0];
-        } catch (const std::exception&) {
-            ok = 0;  // e.g. no peer access between the two devices
-            link.mapped_key = 0;
-        }
-        for (int f : tf) ::close(f);
+    uint64_t n = 0;
+    fdchan_->recv(partner, &n, sizeof(n), none, 0);
+    if (n == ~0ULL) return false;  // the partner cannot export its buffer
+    std::vector<size_t> sizes(n);
+    if (n) fdchan_->recv(partner, sizes.data(), sizes.size() * sizeof(size_t), none, 0);
+    std::vector<int> fds;
+    for (size_t off = 0; off < n; off += 32) {
+        const size_t cnt = std::min<size_t>(32, n - off);
+        uint64_t tag = 0;
+        std::vector<int> part;
+        fdchan_->recv(partner, &tag, sizeof(tag), part, cnt);
+        fds.insert(fds.end(), part.begin(), part.end());
     }
-    if (!link.map || link.mapped_key != theirs[0]) ok = 0;
-    // agree on the outcome before anything is enqueued: one side must never wait in a handshake the other skipped
-    uint64_t their_ok = 0;
-    fdchan_->send(partner, &ok, sizeof(ok), {});
-    fdchan_->recv(partner, &their_ok, sizeof(their_ok), none, 0);
-    if (!their_ok) link.sent_key = 0;        // the partner could not map my shard: resend next time
-    if (!ok || !their_ok) return false;
-    // 2. both sides idle on this shard -> swap -> both sides done
-    const uint64_t half = uint64_t(1) << (n_local_bits - 1);
-    const uint64_t my_bit = 1 - uint64_t((rank_ >> r) & 1);  // rank bit 0 trades its local-bit-1 half, and vice versa
-    const uint64_t lo = (rank_ < partner) ? 0 : half / 2, cnt = (rank_ < partner) ? half / 2 : half - half / 2;
-    handshake(partner);
-    k::peer_swap(ctx, state.amps(), link.map->amps(), lo, cnt, b, int(my_bit));
-    handshake(partner);
-    if (bytes_sent) *bytes_sent += half * sizeof(double2);
+    bool ok = n > 0;
+    if (ok) {
+        try {
+            into.map(device_, fds, sizes);
+        } catch (const std::exception&) {
+            ok = false;  // e.g. no peer access between the two devices
+        }
+    }
+    for (int f : fds) ::close(f);
+    return ok;
+}
+
+void Dist::setup_p2p() {
+    // Everything here may fail on a machine without peer access or without exportable allocations; the outcome is
+    // all-reduced so that either every rank uses the peer-memory path or none does.
+    double ok = fdchan_ ? 1.0 : 0.0;
+    try {
+        if (ok != 0.0) {
+            sync_page_.init(device_, true);
+            sync_page_.ensure(4096, stream_);
+            if (!sync_page_.uses_vmm()) ok = 0.0;
+        }
+        if (ok != 0.0) {
+            cuda_check(cudaMemsetAsync(sync_page_.ptr(), 0, 4096, stream_), "memset(sync page)");
+            cuda_check(cudaHostAlloc(&h_error_, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc(error word)");
+            *h_error_ = 0;
+            cuda_check(cudaHostGetDevicePointer(&d_error_, h_error_, 0), "cudaHostGetDevicePointer");
+            cuda_check(cudaMalloc(&d_block_counter_, sizeof(unsigned int)), "cudaMalloc(block counter)");
+            cuda_check(cudaMemsetAsync(d_block_counter_, 0, sizeof(unsigned int), stream_), "memset(block counter)");
+            cuda_check(cudaStreamSynchronize(stream_), "sync");
+        }
+    } catch (const std::exception&) {
+        ok = 0.0;
+    }
+    // does every rank have a channel and a page?  (decides whether the socket protocol below runs at all)
+    double all = ok;
+    {
+        double v = ok;
+        ensure_buf(1);
+        cuda_check(cudaMemcpyAsync(d_buf_, &v, 8, cudaMemcpyHostToDevice, stream_), "H2D");
+        nccl_check(nccl().AllReduce(d_buf_, d_buf_, 1, ncclDouble, ncclMin, static_cast<ncclComm_t>(comm_), stream_),
+                   "ncclAllReduce(min)");
+        cuda_check(cudaMemcpyAsync(&all, d_buf_, 8, cudaMemcpyDeviceToHost, stream_), "D2H");
+        cuda_check(cudaStreamSynchronize(stream_), "sync");
+    }
+    if (all == 0.0) {
+        fdchan_.reset();
+        return;
+    }
+    // pairwise: trade sync pages with every other rank (XOR order: both ranks of a pair reach each other in the same round)
+    for (int k = 1; k < world_; ++k) {
+        const int partner = rank_ ^ k;
+        PeerLink& link = links_[partner];
+        send_chunks(partner, sync_page_);
+        link.sync_map.reset(new PeerMapping());
+        if (!recv_chunks(partner, *link.sync_map)) ok = 0.0;
+    }
+    {
+        double v = ok;
+        cuda_check(cudaMemcpyAsync(d_buf_, &v, 8, cudaMemcpyHostToDevice, stream_), "H2D");
+        nccl_check(nccl().AllReduce(d_buf_, d_buf_, 1, ncclDouble, ncclMin, static_cast<ncclComm_t>(comm_), stream_),
+                   "ncclAllReduce(min)");
+        cuda_check(cudaMemcpyAsync(&all, d_buf_, 8, cudaMemcpyDeviceToHost, stream_), "D2H");
+        cuda_check(cudaStreamSynchronize(stream_), "sync");
+    }
+    p2p_ok_ = all != 0.0;
+    if (!p2p_ok_) {
+        links_.clear();
+        fdchan_.reset();
+    }
+}
+
+// Make sure this rank has `partner`'s current state buffer mapped and vice versa.  The receiver drives: each side names
+// the buffer it is going to use (layout key), the other side answers whether it already has it mapped, and only then do
+// descriptors travel — so an evicted or stale mapping can never be used by mistake.  Returns the pairwise outcome.
+bool Dist::sync_mapping(int partner, const GrowBuffer& state, PeerMapping** out) {
+    PeerLink& link = links_[partner];
+    std::vector<int> none;
+    const uint64_t my_key = state.layout_key();
+    uint64_t their_key = 0;
+    fdchan_->send(partner, &my_key, sizeof(my_key), {});
+    fdchan_->recv(partner, &their_key, sizeof(their_key), none, 0);
+    uint64_t have = link.find(their_key) ? 1 : 0, they_have = 0;
+    fdchan_->send(partner, &have, sizeof(have), {});
+    fdchan_->recv(partner, &they_have, sizeof(they_have), none, 0);
+    if (!they_have) send_chunks(partner, state);
+    bool ok = true;
+    if (!have) {
+        std::unique_ptr<PeerMapping> m(new PeerMapping());
+        ok = recv_chunks(partner, *m);
+        if (ok) {
+            // the partner rotates between three buffers (state + two scratch copies): keep that many mappings
+            if (link.maps.size() >= 3) link.maps.erase(link.maps.begin());
+            link.maps.emplace_back(their_key, std::move(m));
+        }
+    }
+    *out = ok ? link.find(their_key) : nullptr;
+    return ok;
+}
+
+bool Dist::prepare_exchange(const std::vector<std::pair<int, int>>& swaps, const GrowBuffer& state, int device) {
+    (void)device;
+    if (!p2p_ok_ || swaps.empty() || swaps.size() > 3) return false;
+    cur_ = Prepared();
+    cur_.peers = plan_exchange(rank_, swaps);
+    if (cur_.peers.size() > size_t(k::kMaxExchangePeers)) return false;
+    uint64_t my_ok = state.uses_vmm() ? 1 : 0;
+    for (auto& pr : cur_.peers) {
+        PeerMapping* m = nullptr;
+        if (!sync_mapping(pr.peer, state, &m)) my_ok = 0;
+        cur_.maps.push_back(m);
+    }
+    // the group agrees: one member must never wait in a kernel for a member that took the other path
+    std::vector<int> none;
+    uint64_t group_ok = my_ok;
+    for (auto& pr : cur_.peers) fdchan_->send(pr.peer, &my_ok, sizeof(my_ok), {});
+    for (auto& pr : cur_.peers) {
+        uint64_t theirs = 0;
+        fdchan_->recv(pr.peer, &theirs, sizeof(theirs), none, 0);
+        group_ok &= theirs;
+    }
+    if (!group_ok) return false;
+    cur_.mine = state.amps();
+    cur_.in_pattern = 0;
+    for (auto& sw : swaps) {
+        cur_.in_pattern |= uint64_t((rank_ >> sw.first) & 1) << sw.second;
+        cur_.local_bits.push_back(sw.second);
+    }
+    std::sort(cur_.local_bits.begin(), cur_.local_bits.end());
     return true;
+}
+
+void Dist::exchange_slice(const k::Slice& slice, int n_local_bits, int sm_count, uint64_t* bytes_sent) {
+    k::ExchangeArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.mine = cur_.mine;
+    a.n_peers = int(cur_.peers.size());
+    // ascending merge of the exchanged bits and the slice bits
+    size_t e = 0;
+    int f = 0, n = 0;
+    while (e < cur_.local_bits.size() || f < slice.n) {
+        if (n >= 16) throw std::runtime_error("exchange_slice: too many fixed bits");
+        if (f >= slice.n || (e < cur_.local_bits.size() && cur_.local_bits[e] < int(slice.pos[f])))
+            a.pos[n++] = uint8_t(cur_.local_bits[e++]);
+        else
+            a.pos[n++] = slice.pos[f++];
+    }
+    a.n_pos = n;
+    a.count = uint64_t(1) << (n_local_bits - n);
+    a.in_pattern = cur_.in_pattern | slice.val;
+    a.sync = 1;
+    a.my_rank = rank_;
+    a.my_flags = reinterpret_cast<unsigned long long*>(sync_page_.ptr());
+    a.block_counter = d_block_counter_;
+    a.host_error = d_error_;
+    for (int p = 0; p < a.n_peers; ++p) {
+        const int peer = cur_.peers[p].peer;
+        PeerLink& link = links_[peer];
+        a.peer[p] = cur_.maps[p]->amps();
+        a.out_pattern[p] = cur_.peers[p].pattern | slice.val;
+        a.lower[p] = rank_ < peer ? 1 : 0;
+        a.peer_rank[p] = peer;
+        a.epoch[p] = ++link.epoch;
+        a.peer_flags[p] = reinterpret_cast<unsigned long long*>(link.sync_map->amps());
+    }
+    // fault injection for the parity checks (tests/dist_check.py, bench.py's parity block): leave the sub-block of the
+    // last peer where it is — a wrong permutation that preserves the norm, which only an amplitude comparison can see
+    static const bool broken = [] {
+        const char* e = getenv("PQB_TEST_BREAK_REMAP");
+        return e && e[0] == '1';
+    }();
+    if (broken) --a.n_peers;
+    if (a.n_peers > 0) k::peer_exchange(comm_stream_, a, sm_count);
+    if (bytes_sent) *bytes_sent += uint64_t(a.n_peers) * a.count * sizeof(double2);
 }
 
 void Dist::swap_bits_multi(const std::vector<std::pair<int, int>>& swaps, double2* shard, int n_local_bits,

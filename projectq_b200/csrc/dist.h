@@ -56,7 +56,7 @@ std::vector<ExchangePeer> plan_exchange(int rank, const std::vector<std::pair<in
 
 class Dist {
 public:
-    Dist(int rank, int world, const void* nccl_unique_id, cudaStream_t stream);
+    Dist(int rank, int world, const void* nccl_unique_id, cudaStream_t stream, int device);
     ~Dist();
 
     int rank_bits() const { return g_; }
@@ -75,12 +75,22 @@ public:
     void swap_bits_multi(const std::vector<std::pair<int, int>>& swaps, double2* shard, int n_local_bits, double2* staging,
                          uint64_t staging_amps, uint64_t* bytes_sent);
 
-    // Peer-memory exchange (opt-in, PQB_REMAP_P2P=1): map the partner's shard into this process (VMM handles exported as
-    // file descriptors and passed over a Unix socket) and swap the two halves with one kernel.  Returns false if peer
-    // mapping is not possible (then the caller uses the NCCL path).
-    bool p2p_enabled() const { return fdchan_ != nullptr; }
-    bool swap_bits_p2p(int r, int b, const GrowBuffer& state, int n_local_bits, int device, const k::Ctx& ctx,
-                       uint64_t* bytes_sent);
+    // ---- peer-memory exchange (default; PQB_REMAP_P2P=0 switches it off) ------------------------------------------
+    // Every rank maps the shards of the ranks it exchanges with (VMM handles exported as file descriptors and passed over
+    // a Unix socket) and the whole remap — any number of (rank bit, local bit) pairs at once — is one kernel per rank
+    // (k::peer_exchange) on a dedicated high-priority stream, ordered across GPUs by flags in peer-mapped sync pages.
+    bool p2p_enabled() const { return p2p_ok_; }
+    // Host-side preparation of an exchange of `swaps` on `state`: every member of the exchange group makes sure it has
+    // every other member's current shard mapped, and the group agrees on the outcome.  false -> every member uses the NCCL
+    // path for this remap.  Collective over the group (SPMD: all ranks call it with the same swaps).
+    bool prepare_exchange(const std::vector<std::pair<int, int>>& swaps, const GrowBuffer& state, int device);
+    // Enqueue the exchange of one slice of the shard on comm_stream() (the whole shard when slice.n == 0).  The caller
+    // orders it after the passes that precede it (cudaStreamWaitEvent on comm_stream()) and waits for an event recorded
+    // behind it before touching the slice again.
+    void exchange_slice(const k::Slice& slice, int n_local_bits, int sm_count, uint64_t* bytes_sent);
+    cudaStream_t comm_stream() const { return comm_stream_; }
+    // non-zero once a cross-GPU wait inside an exchange kernel timed out (the state is then undefined)
+    int exchange_error() const { return h_error_ ? *h_error_ : 0; }
 
     double allreduce_sum(double v);
     void allreduce_sum_vec(double* v, size_t n);  // host vector, in place
@@ -98,13 +108,34 @@ private:
     cudaEvent_t ready_ = nullptr;
     void* comm_ = nullptr;
     struct PeerLink {
-        std::unique_ptr<PeerMapping> map;
-        uint64_t mapped_key = 0;  // layout key of the partner buffer currently mapped
-        uint64_t sent_key = 0;    // layout key of my buffer the partner has mapped
+        // the partner's state buffers mapped into this process, by the partner's layout key (its three buffers rotate)
+        std::vector<std::pair<uint64_t, std::unique_ptr<PeerMapping>>> maps;
+        std::unique_ptr<PeerMapping> sync_map;  // the partner's sync page
+        unsigned long long epoch = 0;           // exchanges done with this partner (the same number on both sides)
+        PeerMapping* find(uint64_t key);
     };
     std::unique_ptr<FdChannel> fdchan_;
     std::map<int, PeerLink> links_;
-    void handshake(int peer);  // stream-ordered rendezvous with one partner
+    bool p2p_ok_ = false;
+    int device_ = 0;
+    cudaStream_t comm_stream_ = nullptr;       // exchange kernels (highest priority)
+    GrowBuffer sync_page_;                      // arrive/done flags, mapped by every peer
+    int* h_error_ = nullptr;                    // mapped pinned host word written by a kernel whose spin timed out
+    int* d_error_ = nullptr;
+    unsigned int* d_block_counter_ = nullptr;
+    void setup_p2p();
+    bool sync_mapping(int partner, const GrowBuffer& state, PeerMapping** out);
+    void send_chunks(int partner, const GrowBuffer& buf);
+    bool recv_chunks(int partner, PeerMapping& into);
+    // the exchange prepared by prepare_exchange
+    struct Prepared {
+        std::vector<ExchangePeer> peers;
+        std::vector<PeerMapping*> maps;
+        std::vector<int> local_bits;  // ascending exchanged local bits
+        uint64_t in_pattern = 0;
+        double2* mine = nullptr;
+    } cur_;
+    void handshake(int peer);  // stream-ordered rendezvous with one partner (NCCL path)
     double* d_buf_ = nullptr;  // device staging for scalar collectives
     size_t d_buf_doubles_ = 0;
     void ensure_buf(size_t n);

@@ -54,14 +54,14 @@ Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
     PQB_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     PQB_CHECK(cudaEventCreate(&ev0_));
     PQB_CHECK(cudaEventCreate(&ev1_));
-    for (auto& b : buf_) b.init(device_);
+    for (auto& b : buf_) b.init(device_, /*exportable=*/world_ > 1);
     PQB_CHECK(cudaMalloc(&d_partials_, sizeof(double) * k::kReducePartials));
     PQB_CHECK(cudaMalloc(&d_scalars_, sizeof(double) * kScalarDoubles));
     PQB_CHECK(cudaMallocHost(&h_pinned_, sizeof(double) * kScalarDoubles));
 
     if (world_ > 1) {
         if (!o.nccl_unique_id) throw ValueErr("pqb_create: nccl_unique_id is required when world_size > 1");
-        dist_.reset(new Dist(rank_, world_, o.nccl_unique_id, stream_));
+        dist_.reset(new Dist(rank_, world_, o.nccl_unique_id, stream_, device_));
     }
 
     // |psi> = 1 on one amplitude (simulator.hpp:48-50).  In a sharded run every rank bit starts free: the single
@@ -80,6 +80,9 @@ Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
 
 Engine::~Engine() {
     if (stream_) cudaStreamSynchronize(stream_);
+    if (dist_ && dist_->comm_stream()) cudaStreamSynchronize(dist_->comm_stream());
+    for (auto e : used_events_) cudaEventDestroy(e);
+    for (auto e : free_events_) cudaEventDestroy(e);
     dist_.reset();
     if (d_partials_) cudaFree(d_partials_);
     if (d_scalars_) cudaFree(d_scalars_);
@@ -145,7 +148,74 @@ bool Engine::split_mask(uint64_t lmask, uint64_t lval, uint64_t* local_mask, uin
 double Engine::read_scalar(const double* d_ptr) {
     PQB_CHECK(cudaMemcpyAsync(h_pinned_, d_ptr, sizeof(double), cudaMemcpyDeviceToHost, stream_));
     PQB_CHECK(cudaStreamSynchronize(stream_));
+    check_exchange_error();
     return h_pinned_[0];
+}
+
+void Engine::check_exchange_error() {
+    if (dist_ && dist_->exchange_error())
+        throw CudaErr("global<->local remap: a peer GPU did not answer within the time limit (exchange kernel wait code " +
+                      std::to_string(dist_->exchange_error()) + "); the state is undefined");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// events and deferred timers
+// ---------------------------------------------------------------------------------------------------------------
+cudaEvent_t Engine::get_event() {
+    if (used_events_.size() >= 16384) harvest_timers(true);
+    cudaEvent_t e;
+    if (!free_events_.empty()) {
+        e = free_events_.back();
+        free_events_.pop_back();
+    } else
+        PQB_CHECK(cudaEventCreate(&e));
+    used_events_.push_back(e);
+    return e;
+}
+
+void Engine::wait_on_main(cudaEvent_t ev) {
+    cudaEvent_t s0 = get_event(), s1 = get_event();
+    PQB_CHECK(cudaEventRecord(s0, stream_));
+    PQB_CHECK(cudaStreamWaitEvent(stream_, ev, 0));
+    PQB_CHECK(cudaEventRecord(s1, stream_));
+    timers_.push_back(Timer{s0, s1, T_STALL});
+}
+
+void Engine::harvest_timers(bool synchronize) {
+    if (used_events_.empty()) return;
+    if (synchronize) {
+        PQB_CHECK(cudaStreamSynchronize(stream_));
+        if (dist_ && dist_->comm_stream()) PQB_CHECK(cudaStreamSynchronize(dist_->comm_stream()));
+    }
+    for (auto& t : timers_) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        if (t.kind == T_STALL)
+            stats_.remap_ms += ms;
+        else if (t.kind == T_COMM)
+            stats_.remap_comm_ms += ms;
+        else if (t.kind == T_DIAG)
+            stats_.diag_ms += ms;
+        else if (t.kind >= 0 && t.kind < 6)
+            stats_.pass_ms[t.kind] += ms;
+    }
+    timers_.clear();
+    free_events_.insert(free_events_.end(), used_events_.begin(), used_events_.end());
+    used_events_.clear();
+}
+
+void Engine::get_stats(pqb_stats* out) {
+    harvest_timers(true);
+    check_exchange_error();
+    *out = stats_;
+}
+
+void Engine::reset_stats() {
+    harvest_timers(true);
+    stats_ = pqb_stats{};
 }
 
 double Engine::allreduce_sum(double v) { return dist_ ? dist_->allreduce_sum(v) : v; }
@@ -313,59 +383,89 @@ void Engine::apply_controlled_gate(const double* m, const uint32_t* ids, size_t 
     if (fuser_.pending() >= kMaxPending) run();
 }
 
-void Engine::apply_pass(const FusedPass& p) {
+uint64_t Engine::Launch::touched() const {
+    uint64_t m = 0;
+    if (kind == NONE) return 0;
+    for (int l = 0; l < k; ++l) m |= uint64_t(1) << tpos[l];
+    for (int l = 0; l < n_ctrl; ++l) m |= uint64_t(1) << cpos[l];
+    return m;
+}
+
+Engine::Launch Engine::resolve_pass(const FusedPass& p) {
+    Launch out;
     const int kq = int(p.targets.size());
     if (kq > k::kMaxDense) throw ValueErr("Gates with more than 5 qubits are not supported!");
-    uint8_t cpos[64];
     // controls on rank bits switch whole ranks on or off; controls on local bits become the kernel's control mask
     int ncl = 0;
     bool active = true;
     for (auto c : p.ctrls) {
         const uint32_t lp = map_.at(c);
         if (is_local(lp))
-            cpos[ncl++] = loc_[lp];
+            out.cpos[ncl++] = loc_[lp];
         else if (!((rank_ >> (loc_[lp] - 64)) & 1))
             active = false;
     }
     if (dist_ && (uint64_t(rank_) & dist_->free_rank_bits_mask()) != 0) active = false;  // all-zero shard
-    std::sort(cpos, cpos + ncl);
+    std::sort(out.cpos, out.cpos + ncl);
+    out.n_ctrl = ncl;
     const size_t D = size_t(1) << kq;
     if (p.diagonal) {
         // a diagonal pass needs no remap: targets on rank bits just select a slice of the diagonal for this rank
         ++stats_.diag_passes;
-        if (!active) return;
-        uint8_t tl[8];
+        if (!active) return out;
         int which[8], kl = 0;
         size_t fixed = 0;
         for (int l = 0; l < kq; ++l) {
             const uint32_t lp = map_.at(p.targets[l]);
             if (is_local(lp)) {
-                tl[kl] = loc_[lp];
+                out.tpos[kl] = loc_[lp];
                 which[kl++] = l;
             } else if ((rank_ >> (loc_[lp] - 64)) & 1)
                 fixed |= size_t(1) << l;
         }
-        double d[64];
+        out.m.resize(size_t(2) << kl);
         for (size_t v = 0; v < (size_t(1) << kl); ++v) {
             size_t idx = fixed;
             for (int j = 0; j < kl; ++j)
                 if ((v >> j) & 1) idx |= size_t(1) << which[j];
-            d[2 * v] = p.m[idx * D + idx].real();
-            d[2 * v + 1] = p.m[idx * D + idx].imag();
+            out.m[2 * v] = p.m[idx * D + idx].real();
+            out.m[2 * v + 1] = p.m[idx * D + idx].imag();
         }
-        k::apply_diagonal(ctx(), psi(), L_, kl, tl, ncl, cpos, d);
-        return;
+        out.k = kl;
+        out.kind = Launch::DIAG;
+        return out;
     }
     ++stats_.dense_passes[kq];
-    if (!active) return;
-    uint8_t tpos[8];
+    if (!active) return out;
     for (int l = 0; l < kq; ++l) {
         const uint32_t lp = map_.at(p.targets[l]);
         if (!is_local(lp)) throw RuntimeErr("internal: dense target on a rank bit was not remapped");
-        tpos[l] = loc_[lp];
-        if (l > 0 && tpos[l] <= tpos[l - 1]) throw RuntimeErr("internal: pass targets are not in ascending bit order");
+        out.tpos[l] = loc_[lp];
+        if (l > 0 && out.tpos[l] <= out.tpos[l - 1]) throw RuntimeErr("internal: pass targets are not in ascending bit order");
     }
-    k::apply_dense(ctx(), psi(), L_, kq, tpos, ncl, cpos, reinterpret_cast<const double*>(p.m.data()));
+    out.k = kq;
+    out.kind = Launch::DENSE;
+    const double* m = reinterpret_cast<const double*>(p.m.data());
+    out.m.assign(m, m + 2 * D * D);
+    return out;
+}
+
+void Engine::launch(const Launch& l, const k::Slice& slice) {
+    if (l.kind == Launch::NONE) return;
+    cudaEvent_t e0 = nullptr;
+    if (profiling_) {
+        e0 = get_event();
+        PQB_CHECK(cudaEventRecord(e0, stream_));
+    }
+    if (l.kind == Launch::DIAG)
+        k::apply_diagonal(ctx(), psi(), L_, l.k, l.tpos, l.n_ctrl, l.cpos, l.m.data(), slice);
+    else
+        k::apply_dense(ctx(), psi(), L_, l.k, l.tpos, l.n_ctrl, l.cpos, l.m.data(), slice);
+    if (profiling_) {
+        cudaEvent_t e1 = get_event();
+        PQB_CHECK(cudaEventRecord(e1, stream_));
+        timers_.push_back(Timer{e0, e1, l.kind == Launch::DIAG ? int(T_DIAG) : l.k});
+    }
 }
 
 // bring the given logical positions onto local bits (global<->local qubit remap over NVLink)
@@ -381,10 +481,12 @@ void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uin
     } catch (const std::runtime_error& e) {
         throw RuntimeErr(e.what());
     }
-    // A qubit that leaves from a low local bit leaves in runs of a few bytes: the exchange then has to gather/scatter
-    // through staging slots and was measured at 240-340 GB/s per direction (bit 0: every 32-byte sector is half used),
-    // against 515-570 GB/s for the contiguous halves of a high bit.  So first move the leaving qubit onto the highest free
-    // local bit with one local pass (16 B/amplitude at HBM speed, ~25 ms on a 128 GiB shard), then exchange that bit.
+    // A qubit that leaves from a low local bit leaves in runs of a few bytes.  The NCCL path then has to gather/scatter
+    // through staging slots (measured 240-340 GB/s per direction; bit 0: every 32-byte sector is half used) against
+    // 515-570 GB/s for the contiguous halves of a high bit; the peer-memory kernel only needs runs of a full 128-byte line
+    // (bit 3 and up).  So first move the leaving qubit onto the highest free local bit with one local pass (16 B/amplitude
+    // at HBM speed, ~25 ms on a 128 GiB shard), then exchange that bit.  The incoming qubit lands on that high bit and is
+    // usually the next to leave, so this is paid once, not per remap.
     // plan_remap has already updated loc_ as if the exchange happened at the low bit; the bookkeeping below redirects it.
     if (L_ >= 2) {
         std::vector<int> taken;  // local bits that take part in this remap
@@ -392,7 +494,7 @@ void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uin
         int t = L_ - 1;
         for (auto& sw : swaps) {
             const int b = sw.second;
-            if (b >= L_ - int(swaps.size())) continue;  // already among the top bits
+            if (!leaves_from_low_bit(b, swaps.size())) continue;
             while (t >= 0 && std::find(taken.begin(), taken.end(), t) != taken.end()) --t;
             if (t <= b) break;
             int incoming = -1, at_t = -1;  // logical positions: the qubit plan_remap placed on b, the qubit sitting on t
@@ -407,48 +509,94 @@ void Engine::make_local(const std::vector<uint32_t>& need, const std::vector<uin
             taken.push_back(t);
         }
     }
-    // staging: a bounded slice of the second scratch buffer (the state itself may fill most of HBM)
-    const uint64_t want = std::min<uint64_t>(local_amps() >> 1, uint64_t(1) << 26);  // <= 1 GiB
-    ensure_scratch(*scratch2_, std::max<uint64_t>(want, 1) * sizeof(double2));
-    // ev0_/ev1_ belong to the user-facing stopwatch (timer_start/timer_stop), so remaps time themselves with their own pair
-    if (!remap_e0_) {
-        PQB_CHECK(cudaEventCreate(&remap_e0_));
-        PQB_CHECK(cudaEventCreate(&remap_e1_));
-    }
-    cudaEvent_t e0 = remap_e0_, e1 = remap_e1_;
-    PQB_CHECK(cudaEventRecord(e0, stream_));
+    serial_exchange(swaps);
+}
+
+// one remap, not overlapped with anything: the peer-memory exchange kernel (all bits at once) when every member of the
+// exchange group can map the others' shards, NCCL send/recv through a staging slice otherwise
+void Engine::serial_exchange(const std::vector<std::pair<int, int>>& swaps) {
+    if (swaps.empty()) return;
+    ++stats_.remaps;
+    stats_.remap_qubits += swaps.size();
     try {
-        // Several bits at once can go as one all-to-all (pairwise rounds over sub-blocks, 1 - 2^-g of the shard instead of
-        // g/2).  Measured on 4 GPUs it is slower so far (213-245 GB/s per direction against 440-570 for single-bit
-        // exchanges, so 60 ms against 39 ms for two bits of a 16 GiB shard): opt-in (PQB_REMAP_MULTI=1) until that is
-        // understood; the default exchanges bit by bit.
+        if (dist_->prepare_exchange(swaps, *state_, device_)) {
+            cudaEvent_t before = get_event(), x0 = get_event(), x1 = get_event();
+            PQB_CHECK(cudaEventRecord(before, stream_));
+            PQB_CHECK(cudaStreamWaitEvent(dist_->comm_stream(), before, 0));
+            PQB_CHECK(cudaEventRecord(x0, dist_->comm_stream()));
+            dist_->exchange_slice(k::Slice(), L_, sm_count_, &stats_.remap_bytes_sent);
+            ++stats_.kernel_launches;
+            PQB_CHECK(cudaEventRecord(x1, dist_->comm_stream()));
+            timers_.push_back(Timer{x0, x1, T_COMM});
+            wait_on_main(x1);
+            ++stats_.p2p_remaps;
+            return;
+        }
+        // NCCL path.  Staging: a bounded slice of the second scratch buffer (the state itself may fill most of HBM)
+        const uint64_t want = std::min<uint64_t>(local_amps() >> 1, uint64_t(1) << 26);  // <= 1 GiB
+        ensure_scratch(*scratch2_, std::max<uint64_t>(want, 1) * sizeof(double2));
+        cudaEvent_t e0 = get_event(), e1 = get_event();
+        PQB_CHECK(cudaEventRecord(e0, stream_));
+        // Several bits at once can also go as pairwise rounds over sub-blocks (PQB_REMAP_MULTI=1); measured slower than
+        // bit-by-bit exchanges with NCCL on 4 GPUs, so the NCCL path exchanges bit by bit.
         static const bool multi = [] {
             const char* e = getenv("PQB_REMAP_MULTI");
             return e && e[0] == '1';
         }();
-        if (multi && swaps.size() >= 2 && swaps.size() <= 8 && want >= 4) {
+        if (multi && swaps.size() >= 2 && swaps.size() <= 8 && want >= 4)
             dist_->swap_bits_multi(swaps, psi(), L_, scratch2_->amps(), want, &stats_.remap_bytes_sent);
-            ++stats_.remaps;
-        } else {
-            for (auto& sw : swaps) {
-                // opt-in peer-memory exchange (one kernel over NVLink, no staging); NCCL send/recv otherwise
-                if (dist_->p2p_enabled() && L_ >= 2 &&
-                    dist_->swap_bits_p2p(sw.first, sw.second, *state_, L_, device_, ctx(), &stats_.remap_bytes_sent))
-                    ++stats_.p2p_remaps;
-                else
-                    dist_->swap_bits(sw.first, sw.second, psi(), L_, scratch2_->amps(), std::max<uint64_t>(want, 1),
-                                     &stats_.remap_bytes_sent);
-                ++stats_.remaps;
-            }
-        }
+        else
+            for (auto& sw : swaps)
+                dist_->swap_bits(sw.first, sw.second, psi(), L_, scratch2_->amps(), std::max<uint64_t>(want, 1),
+                                 &stats_.remap_bytes_sent);
+        PQB_CHECK(cudaEventRecord(e1, stream_));
+        timers_.push_back(Timer{e0, e1, T_STALL});
+    } catch (const CudaErr&) {
+        throw;
     } catch (const std::runtime_error& e) {
         throw CudaErr(e.what());
     }
-    PQB_CHECK(cudaEventRecord(e1, stream_));
-    PQB_CHECK(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    stats_.remap_ms += ms;
+}
+
+// One remap executed slice by slice.  The slice bits are local bits that neither the exchange nor the passes around it
+// touch, so slice i can receive the last passes before the remap (`tail`), go over NVLink, and receive the first passes
+// after it (`head`) independently of the other slices.  The main stream runs tail(0), tail(1), head(0), tail(2), head(1),
+// ... while the communication stream exchanges slice i as soon as tail(i) is done: the exchange of a slice overlaps the
+// passes on its neighbours, and only the first and last exchange can leave the main stream waiting.
+void Engine::pipelined_exchange(const std::vector<Launch>& tail, const std::vector<Launch>& head,
+                                const std::vector<uint8_t>& slice_bits) {
+    const int s = int(slice_bits.size());
+    const int n_slices = 1 << s;
+    cudaStream_t comm = dist_->comm_stream();
+    auto slice_of = [&](int i) {
+        k::Slice sl;
+        sl.n = s;
+        for (int b = 0; b < s; ++b) sl.pos[b] = slice_bits[b];
+        sl.val = deposit_bits(uint64_t(i), slice_bits.data(), s);
+        return sl;
+    };
+    std::vector<cudaEvent_t> exchanged(n_slices);
+    for (int i = 0; i < n_slices; ++i) {
+        const k::Slice sl = slice_of(i);
+        for (auto& l : tail) launch(l, sl);
+        cudaEvent_t ready = get_event(), x0 = get_event();
+        exchanged[i] = get_event();
+        PQB_CHECK(cudaEventRecord(ready, stream_));
+        PQB_CHECK(cudaStreamWaitEvent(comm, ready, 0));
+        PQB_CHECK(cudaEventRecord(x0, comm));
+        dist_->exchange_slice(sl, L_, sm_count_, &stats_.remap_bytes_sent);
+        ++stats_.kernel_launches;
+        PQB_CHECK(cudaEventRecord(exchanged[i], comm));
+        timers_.push_back(Timer{x0, exchanged[i], T_COMM});
+        if (i >= 1) {
+            wait_on_main(exchanged[i - 1]);
+            const k::Slice prev = slice_of(i - 1);
+            for (auto& l : head) launch(l, prev);
+        }
+    }
+    wait_on_main(exchanged[n_slices - 1]);
+    const k::Slice last = slice_of(n_slices - 1);
+    for (auto& l : head) launch(l, last);
 }
 
 void Engine::run() {
@@ -502,10 +650,11 @@ void Engine::run() {
     }
 }
 
-// Sharded run(): execute everything that touches only on-device qubits, and only then pay for a remap.  The remap brings
-// in the rank-bit qubits of the oldest waiting gate and evicts the local qubits that are needed last (Belady), so a
-// brickwork circuit needs about one remap per global qubit per flush instead of one per layer.
-void Engine::run_sharded() {
+bool Engine::leaves_from_low_bit(int b, size_t n_swaps) const {
+    return dist_->p2p_enabled() ? b < 3 : b < L_ - int(n_swaps);
+}
+
+void Engine::resolve_phase(int width, std::vector<Launch>& out, bool eager, size_t hold) {
     auto key = [this](uint32_t id) -> uint64_t {
         auto it = map_.find(id);
         if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
@@ -516,20 +665,112 @@ void Engine::run_sharded() {
         if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
         return loc_[it->second] >= 64;
     };
+    std::vector<char> done;
+    const std::vector<Cluster> clusters = fuser_.schedule_unblocked(width, blocked, done);
+    for (size_t c = 0; c < clusters.size(); ++c) {
+        Launch l = resolve_pass(fuser_.fuse_cluster(clusters[c], key));
+        if (eager && out.empty() && c + hold < clusters.size())
+            launch(l);  // the GPU works on this pass while the host multiplies the matrices of the next one
+        else
+            out.push_back(std::move(l));
+    }
+    fuser_.remove_done(done);
+}
+
+// Sharded run(): execute everything that touches only on-device qubits, and only then pay for a remap.  The remap brings
+// in the rank-bit qubits of the oldest waiting gate and evicts the local qubits that are needed last (Belady), so a
+// brickwork circuit needs about one remap per flush instead of one per layer.  The remap itself moves all its qubits in
+// one peer-memory exchange and is pipelined slice by slice against the last passes before it and the first passes after
+// it (pipelined_exchange), so that NVLink traffic and HBM-bound passes run at the same time.
+void Engine::run_sharded() {
+    static const int max_slice_bits = [] {
+        const char* e = getenv("PQB_REMAP_SLICE_BITS");  // 0 switches the pipeline off
+        return e ? std::max(0, std::min(4, atoi(e))) : 3;
+    }();
+    constexpr size_t kTail = 3, kHead = 4;  // passes before / after the remap that may run slice by slice
     const int width = fusion_max_ > 0 ? fusion_max_ : 4;
     const InteractionGraph adj = interaction_graph(fuser_);  // of this flush: breaks ties between eviction candidates
     try {
+        std::vector<Launch> held;  // resolved but not yet launched (the candidates for a pipeline's tail)
+        resolve_phase(width, held, true, kTail);
         while (fuser_.pending() > 0) {
-            std::vector<char> done;
-            const std::vector<Cluster> clusters = fuser_.schedule_unblocked(width, blocked, done);
-            for (auto& cl : clusters) apply_pass(fuser_.fuse_cluster(cl, key));
-            fuser_.remove_done(done);
-            if (fuser_.pending() == 0) break;
-            RemapChoice choice = choose_remap(fuser_, map_, loc_, adj);
-            const std::vector<uint32_t>& need = choice.need;
-            const std::vector<uint32_t>& victims = choice.victims;
-            make_local(need, &victims);
+            const RemapChoice choice = choose_remap(fuser_, map_, loc_, adj);
+            // plan on a copy of the layout first: a remap that needs a local pre-pass is not pipelined
+            std::vector<uint8_t> planned = loc_;
+            std::vector<std::pair<int, int>> swaps;
+            try {
+                swaps = plan_remap(planned, L_, choice.need, &choice.victims);
+            } catch (const std::runtime_error& e) {
+                throw RuntimeErr(e.what());
+            }
+            bool pipelined = dist_->p2p_enabled() && max_slice_bits > 0 && !swaps.empty() && swaps.size() <= 3 &&
+                             L_ - int(swaps.size()) >= 2;
+            uint64_t exchanged_bits = 0;
+            for (auto& sw : swaps) {
+                if (leaves_from_low_bit(sw.second, swaps.size())) pipelined = false;
+                exchanged_bits |= uint64_t(1) << sw.second;
+            }
+            if (pipelined) {
+                try {
+                    pipelined = dist_->prepare_exchange(swaps, *state_, device_);  // collective: same decision on every rank
+                } catch (const std::runtime_error& e) {
+                    throw CudaErr(e.what());
+                }
+            }
+            if (!pipelined) {
+                for (auto& l : held) launch(l);
+                held.clear();
+                make_local(choice.need, &choice.victims);
+                resolve_phase(width, held, true, kTail);
+                continue;
+            }
+            loc_ = planned;
+            ++stats_.remaps;
+            ++stats_.p2p_remaps;
+            ++stats_.pipelined_remaps;
+            stats_.remap_qubits += swaps.size();
+            const uint64_t all_local = (uint64_t(1) << L_) - 1;
+            const int want = std::min(max_slice_bits, L_ - int(swaps.size()) - 1);
+            auto free_bits = [&](uint64_t used) { return __builtin_popcountll(all_local & ~used); };
+            // tail: the longest suffix of the held passes that leaves enough untouched bits to slice along
+            size_t n_tail = 0;
+            uint64_t used = exchanged_bits;
+            while (n_tail < held.size() && n_tail < kTail) {
+                const uint64_t u = used | held[held.size() - 1 - n_tail].touched();
+                if (free_bits(u) < want) break;
+                used = u;
+                ++n_tail;
+            }
+            for (size_t i = 0; i + n_tail < held.size(); ++i) launch(held[i]);
+            std::vector<Launch> tail(held.end() - n_tail, held.end());
+            held.clear();
+            // what can run once the exchanged qubits are on-device; resolved while the GPU works through the launches above
+            std::vector<Launch> next;
+            resolve_phase(width, next, false, 0);
+            size_t n_head = 0;
+            while (n_head < next.size() && n_head < kHead) {
+                const uint64_t u = used | next[n_head].touched();
+                if (free_bits(u) < want) break;
+                used = u;
+                ++n_head;
+            }
+            std::vector<uint8_t> slice_bits;
+            if (n_tail + n_head > 0)
+                for (int b = L_ - 1; b >= 0 && int(slice_bits.size()) < want; --b)
+                    if (!((used >> b) & 1)) slice_bits.push_back(uint8_t(b));
+            std::sort(slice_bits.begin(), slice_bits.end());
+            std::vector<Launch> head(next.begin(), next.begin() + n_head);
+            pipelined_exchange(tail, head, slice_bits);
+            // the rest of the phase: everything but the last kTail launches goes out now
+            const size_t n_rest = next.size() - n_head;
+            for (size_t i = 0; i < n_rest; ++i) {
+                if (i + kTail < n_rest)
+                    launch(next[n_head + i]);
+                else
+                    held.push_back(std::move(next[n_head + i]));
+            }
         }
+        for (auto& l : held) launch(l);
     } catch (...) {
         fuser_.clear();
         throw;
@@ -1151,7 +1392,10 @@ void Engine::init_random_state(uint32_t n_qubits, uint64_t seed) {
     k::scale_all(ctx(), psi(), local_amps(), 1.0 / std::sqrt(nrm));
 }
 
-void Engine::synchronize() { PQB_CHECK(cudaStreamSynchronize(stream_)); }
+void Engine::synchronize() {
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+    check_exchange_error();
+}
 
 void Engine::timer_start() { PQB_CHECK(cudaEventRecord(ev0_, stream_)); }
 
@@ -1190,6 +1434,37 @@ double Engine::bench_dense_pass(const double* m, const uint32_t* positions, size
     timer_start();
     for (int r = 0; r < repeats; ++r) k::apply_dense(ctx(), psi(), L_, int(kq), tpos, nc, cpos, m);
     return timer_stop() / repeats;
+}
+
+void Engine::selftest_sliced_pass(const double* m, const uint32_t* positions, size_t kq, uint64_t ctrl_mask,
+                                  uint64_t slice_mask) {
+    run();
+    if (kq == 0 || kq > 5) throw ValueErr("selftest_sliced_pass(): k must be 1..5");
+    Launch l;
+    l.kind = Launch::DENSE;
+    l.k = int(kq);
+    uint64_t used = ctrl_mask;
+    for (size_t i = 0; i < kq; ++i) {
+        if (int(positions[i]) >= L_) throw ValueErr("selftest_sliced_pass(): position outside the local state");
+        l.tpos[i] = uint8_t(positions[i]);
+        used |= uint64_t(1) << positions[i];
+    }
+    if (!std::is_sorted(l.tpos, l.tpos + kq)) throw ValueErr("selftest_sliced_pass(): positions must ascend");
+    if ((used & slice_mask) != 0 || (L_ < 64 && (slice_mask >> L_) != 0))
+        throw ValueErr("selftest_sliced_pass(): slice bits must be free local bits");
+    for (int b = 0; b < L_; ++b)
+        if ((ctrl_mask >> b) & 1) l.cpos[l.n_ctrl++] = uint8_t(b);
+    l.m.assign(m, m + (size_t(2) << (2 * kq)));
+    k::Slice sl;
+    for (int b = 0; b < L_; ++b)
+        if ((slice_mask >> b) & 1) {
+            if (sl.n >= 16) throw ValueErr("selftest_sliced_pass(): more than 16 slice bits");
+            sl.pos[sl.n++] = uint8_t(b);
+        }
+    for (uint64_t v = 0; v < (uint64_t(1) << sl.n); ++v) {
+        sl.val = deposit_bits(v, sl.pos, sl.n);
+        launch(l, sl);
+    }
 }
 
 double Engine::measure_fp64_peak() { return k::measure_fp64_tflops(ctx(), sm_count_); }

@@ -100,10 +100,12 @@ public:
     void synchronize();
     void timer_start();
     double timer_stop();
-    void get_stats(pqb_stats* out) const { *out = stats_; }
-    void reset_stats() { stats_ = pqb_stats{}; }
+    void get_stats(pqb_stats* out);
+    void reset_stats();
+    void set_profiling(bool on) { profiling_ = on; }
     void flush_l2(size_t bytes);
     double bench_dense_pass(const double* m, const uint32_t* positions, size_t k, uint64_t ctrl_mask, int repeats);
+    void selftest_sliced_pass(const double* m, const uint32_t* positions, size_t k, uint64_t ctrl_mask, uint64_t slice_mask);
     double measure_fp64_peak();
     double measure_copy_bandwidth(size_t bytes);
 
@@ -125,8 +127,39 @@ private:
     std::vector<k::PauliTerm> build_terms(const TermsView& t, const uint32_t* ids, size_t n_ids, bool skip_identity,
                                           double* identity_sum_re, double* identity_sum_im);
     void make_local(const std::vector<uint32_t>& logical_positions, const std::vector<uint32_t>* victims = nullptr);
-    void apply_pass(const FusedPass& p);
+    // A fused pass resolved to physical bit positions under the qubit layout that was current when it was resolved; it can
+    // be launched later (and slice by slice) whatever has happened to the layout bookkeeping in between.
+    struct Launch {
+        enum Kind { NONE, DENSE, DIAG } kind = NONE;  // NONE: this rank's control bits switch the pass off
+        int k = 0, n_ctrl = 0;
+        uint8_t tpos[8] = {}, cpos[64] = {};
+        std::vector<double> m;  // DENSE: 2^k x 2^k (re,im) row-major; DIAG: 2^k (re,im)
+        uint64_t touched() const;  // mask of the local bits the launch reads as target or control
+    };
+    Launch resolve_pass(const FusedPass& p);
+    void launch(const Launch& l, const k::Slice& slice = k::Slice());
+    void apply_pass(const FusedPass& p) { launch(resolve_pass(p)); }
     void run_sharded();
+    // schedule everything that can run under the current layout, fuse it and resolve it into `out` (appended); with
+    // `eager` all but the last `hold` launches are issued right away (they cannot be part of a remap pipeline's tail)
+    void resolve_phase(int width, std::vector<Launch>& out, bool eager, size_t hold);
+    void serial_exchange(const std::vector<std::pair<int, int>>& swaps);
+    void pipelined_exchange(const std::vector<Launch>& tail, const std::vector<Launch>& head,
+                            const std::vector<uint8_t>& slice_bits);
+    void check_exchange_error();
+    bool leaves_from_low_bit(int local_bit, size_t n_swaps) const;
+    // CUDA events: a pool, and (start, stop) pairs whose elapsed time is added to a counter once they have completed
+    enum TimerKind { T_PASS0 = 0, T_DIAG = 6, T_STALL = 7, T_COMM = 8 };
+    struct Timer {
+        cudaEvent_t e0, e1;
+        int kind;
+    };
+    cudaEvent_t get_event();
+    void wait_on_main(cudaEvent_t ev);  // main stream waits for ev; the wait is timed as exposed remap time
+    void harvest_timers(bool synchronize);
+    std::vector<cudaEvent_t> free_events_, used_events_;
+    std::vector<Timer> timers_;
+    bool profiling_ = false;
     unsigned long long last_probe_[2] = {~0ULL, ~0ULL};  // result of the last classical probe (bit 0, bit 1)
     double draw_uniform();
 

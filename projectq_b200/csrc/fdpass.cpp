@@ -64,7 +64,7 @@ std::string FdChannel::name_of(int rank) const {
     return buf;
 }
 
-FdChannel::FdChannel(uint64_t run_tag, int rank) : tag_(run_tag), rank_(rank) {
+FdChannel::FdChannel(uint64_t run_tag, int rank, int world) : tag_(run_tag), rank_(rank), world_(world) {
     listen_fd_ = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
     if (listen_fd_ < 0) fail("socket");
     sockaddr_un addr;
@@ -109,8 +109,20 @@ int FdChannel::socket_to(int peer) {
             if (errno == EINTR) continue;
             fail("accept");
         }
+        // only processes of the same user may join: the descriptors passed here give read/write access to the GPU state
+        ucred cred;
+        socklen_t clen = sizeof(cred);
+        if (::getsockopt(fd, SOL_SOCKET, SO_PEERCRED, &cred, &clen) != 0 || cred.uid != ::geteuid()) {
+            ::close(fd);
+            continue;
+        }
         int32_t who = -1;
         read_all(fd, &who, sizeof(who));
+        // a rank connects only to lower ranks, and only once
+        if (who <= rank_ || who >= world_ || conn_.count(who)) {
+            ::close(fd);
+            continue;
+        }
         conn_[who] = fd;
         if (who == peer) return fd;
     }

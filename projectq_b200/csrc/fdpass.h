@@ -15,7 +15,7 @@ namespace pqb {
 
 class FdChannel {
 public:
-    FdChannel(uint64_t run_tag, int rank);
+    FdChannel(uint64_t run_tag, int rank, int world);
     ~FdChannel();
     FdChannel(const FdChannel&) = delete;
     FdChannel& operator=(const FdChannel&) = delete;
@@ -29,7 +29,7 @@ private:
     int socket_to(int peer);  // connects (higher rank) or accepts (lower rank) on first use
     std::string name_of(int rank) const;
     uint64_t tag_;
-    int rank_;
+    int rank_, world_;
     int listen_fd_ = -1;
     std::map<int, int> conn_;  // peer -> connected socket
 };

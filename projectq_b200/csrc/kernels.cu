@@ -271,21 +271,36 @@ static int lowbits_run(const DenseArgs<K>& args, int n_bits) {
     return cbits;
 }
 
+// A launch can be restricted to a slice of the state: the bits in slice.pos are held at the values in slice.val (other
+// bits of val are 0).  To the kernel a slice bit is just one more inserted bit whose value is OR-ed in — exactly how a
+// control works, except that the value may be 0 — so slicing costs nothing.  The sharded engine uses it to run the passes
+// around a global<->local remap slice by slice while the other slices are on the NVLink wire.
 template <int K>
 static void fill_dense_args(DenseArgs<K>& args, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
-                            const double* m_host) {
+                            const double* m_host, const Slice& slice) {
     constexpr int D = 1 << K;
     for (int i = 0; i < D * D; ++i) args.m[i] = make_double2(m_host[2 * i], m_host[2 * i + 1]);
-    // ascending merge of target and control positions
-    int a = 0, b = 0, n = 0;
-    uint64_t cmask = 0;
-    while (a < K || b < n_ctrl) {
-        if (b >= n_ctrl || (a < K && tpos[a] < cpos[b]))
-            args.ins_pos[n++] = tpos[a++];
-        else {
-            cmask |= uint64_t(1) << cpos[b];
-            args.ins_pos[n++] = cpos[b++];
+    // ascending merge of target, control and slice positions
+    uint8_t fixed[64 + 16];
+    int nf = 0;
+    uint64_t cmask = slice.val;
+    {
+        int b = 0, f = 0;
+        while (b < n_ctrl || f < slice.n) {
+            if (f >= slice.n || (b < n_ctrl && cpos[b] < slice.pos[f])) {
+                cmask |= uint64_t(1) << cpos[b];
+                fixed[nf++] = cpos[b++];
+            } else
+                fixed[nf++] = slice.pos[f++];
         }
+    }
+    if (K + nf > 64) throw std::invalid_argument("apply_dense: too many target/control/slice bits");
+    int a = 0, b = 0, n = 0;
+    while (a < K || b < nf) {
+        if (b >= nf || (a < K && tpos[a] < fixed[b]))
+            args.ins_pos[n++] = tpos[a++];
+        else
+            args.ins_pos[n++] = fixed[b++];
     }
     args.n_ins = n;
     args.ctrl_mask = cmask;
@@ -306,11 +321,11 @@ static void launch_dense_mode(const Ctx& c, double2* psi, const DenseArgs<K>& ar
 // U0/T0: unroll and block size of the 128-bit variant
 template <int K, int U0, int T0>
 static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
-                         const double* m_host) {
+                         const double* m_host, const Slice& slice) {
     DenseArgs<K> args;  // parameter block (copied by the launch); on the stack so concurrent engines do not share it
     const bool bit0_target = tpos[0] == 0;
     if (bit0_target) {
-        fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host);
+        fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host, slice);
         if constexpr (K == 3) {
             // Measured at 28 qubits (profiles/): k = 3 {0,1,2} 1.60 -> 1.23 ms with the transposing kernel.  At k = 4, 5 it
             // loses (1.75 -> 1.77-2.0 ms, 3.75 -> 3.85-4.5 ms): 64+ shared-memory 128-bit operations per thread make the
@@ -321,19 +336,19 @@ static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* 
         }
         launch_dense_mode<K, 1, 1, (K >= 5 ? 128 : 256), (K == 3 ? 2 : (K <= 2 ? 4 : 3))>(c, psi, args);
     } else {
-        fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host);
+        fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host, slice);
         launch_dense_mode<K, 0, U0, T0, (K == 3 ? 2 : (K <= 2 ? 3 : 3))>(c, psi, args);
     }
 }
 
 void apply_dense(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
-                 const double* m_host) {
+                 const double* m_host, const Slice& slice) {
     switch (k) {
-        case 1: launch_dense<1, 4, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
-        case 2: launch_dense<2, 2, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
-        case 3: launch_dense<3, 2, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
-        case 4: launch_dense<4, 1, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
-        case 5: launch_dense<5, 1, 128>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host); break;
+        case 1: launch_dense<1, 4, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host, slice); break;
+        case 2: launch_dense<2, 2, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host, slice); break;
+        case 3: launch_dense<3, 2, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host, slice); break;
+        case 4: launch_dense<4, 1, 256>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host, slice); break;
+        case 5: launch_dense<5, 1, 128>(c, psi, n_bits, tpos, n_ctrl, cpos, m_host, slice); break;
         default: throw std::invalid_argument("Gates with more than 5 qubits are not supported!");
     }
 }
@@ -361,18 +376,25 @@ __global__ void __launch_bounds__(256) apply_diag_kernel(double2* __restrict__ p
 }
 
 void apply_diagonal(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl,
-                    const uint8_t* cpos, const double* d_host) {
+                    const uint8_t* cpos, const double* d_host, const Slice& slice) {
     if (k > 5) throw std::invalid_argument("apply_diagonal: k > 5");
+    if (n_ctrl + slice.n > 64) throw std::invalid_argument("apply_diagonal: too many control/slice bits");
     DiagArgs a{};
     for (int i = 0; i < (1 << k); ++i) a.d[i] = make_double2(d_host[2 * i], d_host[2 * i + 1]);
     a.k = k;
-    a.n_ctrl = n_ctrl;
-    a.ctrl_mask = 0;
+    a.ctrl_mask = slice.val;
     for (int l = 0; l < k; ++l) a.tpos[l] = tpos[l];
-    for (int l = 0; l < n_ctrl; ++l) {
-        a.cpos[l] = cpos[l];
-        a.ctrl_mask |= uint64_t(1) << cpos[l];
+    // fixed bits = controls (value 1) and slice bits (value from slice.val), ascending
+    int b = 0, f = 0, n = 0;
+    while (b < n_ctrl || f < slice.n) {
+        if (f >= slice.n || (b < n_ctrl && cpos[b] < slice.pos[f])) {
+            a.ctrl_mask |= uint64_t(1) << cpos[b];
+            a.cpos[n++] = cpos[b++];
+        } else
+            a.cpos[n++] = slice.pos[f++];
     }
+    a.n_ctrl = n;
+    n_ctrl = n;
     a.n_items = uint64_t(1) << (n_bits - n_ctrl);
     uint64_t blocks = (a.n_items + 256 * 4 - 1) / (256 * 4);
     if (blocks > 148 * 32) blocks = 148 * 32;
@@ -586,30 +608,125 @@ void swap_local_bits(const Ctx& c, double2* psi, int n_bits, int b0, int b1) {
     launched(c);
 }
 
-// Global<->local qubit exchange over peer-mapped memory: amplitude j of my outgoing half (local bit `pos` == my_bit)
-// trades places with amplitude j of the partner's outgoing half (bit `pos` == 1 - my_bit) in ONE kernel — a remote
-// 128-bit load and a remote 128-bit store per amplitude over NVLink, no staging buffer, no second copy.  Both ranks of a
-// pair run it, each on its own half of the j range, so both directions of the link carry loads and stores.
-__global__ void __launch_bounds__(256) peer_swap_kernel(double2* __restrict__ mine, double2* __restrict__ peer,
-                                                        uint64_t first, uint64_t count, int pos, uint64_t my_bit) {
-    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
-    const uint64_t mbit = my_bit << pos, pbit = (my_bit ^ 1) << pos;
-    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += step) {
-        const uint64_t idx = insert_zero_bit(first + j, pos);
-        const double2 a = mine[idx | mbit];
-        const double2 b = peer[idx | pbit];
-        mine[idx | mbit] = b;
-        peer[idx | pbit] = a;
+// ------------------------------------------------------------------------------------------------------------------
+// Global<->local qubit remap over peer-mapped memory (NVLink / NVSwitch): the whole exchange in ONE kernel per rank.
+//
+// Exchanging g rank bits with g local bits is an all-to-all inside the group of 2^g ranks that differ only in those rank
+// bits: my sub-block whose exchanged local bits spell a peer's rank-bit values trades places with the peer's sub-block
+// that spells mine (dist.h plan_exchange).  Every rank has the shards of its peers mapped (VMM handles passed as file
+// descriptors), so one thread simply loads amplitude j of both sub-blocks and stores them crosswise — a remote 128-bit
+// load and a remote 128-bit store per amplitude, no staging buffer, no second copy.  The two ranks of a pair split the
+// j range, so each direction of every link carries half read responses and half writes.  Blocks walk the peers round-robin
+// in chunks of 1024 amplitudes, so all 2^g - 1 links are busy at the same time.
+//
+// Cross-GPU ordering is done with flags in peer-mapped "sync pages" instead of host rendezvous:
+//   arrive: a kernel may touch a peer's shard only after the peer has finished everything queued before ITS exchange
+//           kernel (its passes on this slice) — each kernel announces itself to its peers and waits for theirs;
+//   done:   a kernel completes only when every peer's kernel has completed its stores into this rank's shard, so the
+//           stream event recorded after it releases the passes that follow.
+// Flags carry a per-pair epoch (both ranks of a pair count their exchanges), so they never have to be reset.  A spin that
+// lasts longer than kSpinTimeoutNs gives up and raises a host-visible error instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// wait until *flag >= want; false on timeout
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want) {
+    if (ld_acquire_sys(flag) >= want) return true;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < want) {
+        __nanosleep(200);
+        if (global_ns() - t0 > kSpinTimeoutNs) return false;
     }
-    __threadfence_system();
+    return true;
 }
 
-void peer_swap(const Ctx& c, double2* mine, double2* peer, uint64_t first, uint64_t count, int pos, int my_bit) {
-    if (count == 0) return;
-    uint64_t blocks = (count + 256 * 4 - 1) / (256 * 4);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    peer_swap_kernel<<<unsigned(blocks), 256, 0, c.stream>>>(mine, peer, first, count, pos, uint64_t(my_bit ? 1 : 0));
-    launched(c);
+__global__ void __launch_bounds__(256) peer_exchange_kernel(const __grid_constant__ ExchangeArgs a) {
+    const int tid = threadIdx.x;
+    // ---- arrive ----
+    if (a.sync) {
+        if (blockIdx.x == 0 && tid < a.n_peers) {
+            __threadfence_system();
+            st_release_sys(a.peer_flags[tid] + kFlagArrive + a.my_rank, a.epoch[tid]);
+        }
+        if (tid < a.n_peers && !spin_until(a.my_flags + kFlagArrive + a.peer_rank[tid], a.epoch[tid])) *a.host_error = 1;
+        __syncthreads();
+    }
+    // ---- swap ----
+    constexpr uint64_t CH = 1024;  // amplitudes per (block, peer) chunk: 4 per thread
+    const uint64_t lo_cnt = a.count / 2, hi_cnt = a.count - lo_cnt;
+    const uint64_t max_share = hi_cnt;
+    const uint64_t chunks_per_peer = (max_share + CH - 1) / CH;
+    const uint64_t n_chunks = chunks_per_peer * uint64_t(a.n_peers);
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int p = int(c % uint64_t(a.n_peers));
+        const uint64_t jc = c / uint64_t(a.n_peers);
+        const uint64_t first = a.lower[p] ? 0 : lo_cnt, share = a.lower[p] ? lo_cnt : hi_cnt;
+        double2* __restrict__ mine = a.mine;
+        double2* __restrict__ peer = a.peer[p];
+        const uint64_t mp = a.out_pattern[p], pp = a.in_pattern;
+        double2 x[4], y[4];
+        uint64_t idx[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t r = jc * CH + uint64_t(u) * 256 + tid;
+            ok[u] = r < share;
+            if (ok[u]) {
+                idx[u] = insert_zero_bits(first + r, a.pos, a.n_pos);
+                x[u] = __ldcg(mine + (idx[u] | mp));
+                y[u] = __ldcg(peer + (idx[u] | pp));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ok[u]) {
+                __stcg(mine + (idx[u] | mp), y[u]);
+                __stcg(peer + (idx[u] | pp), x[u]);
+            }
+        }
+    }
+    // ---- done ----
+    if (a.sync) {
+        __threadfence_system();
+        __syncthreads();
+        __shared__ bool last;
+        if (tid == 0) last = atomicAdd(a.block_counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last) {
+            if (tid == 0) *a.block_counter = 0;
+            if (tid < a.n_peers) {
+                __threadfence_system();
+                st_release_sys(a.peer_flags[tid] + kFlagDone + a.my_rank, a.epoch[tid]);
+                if (!spin_until(a.my_flags + kFlagDone + a.peer_rank[tid], a.epoch[tid])) *a.host_error = 2;
+            }
+        }
+    }
+}
+
+void peer_exchange(cudaStream_t stream, const ExchangeArgs& a, int sm_count) {
+    if (a.n_peers < 1 || a.n_peers > kMaxExchangePeers) throw std::invalid_argument("peer_exchange: bad peer count");
+    if (a.n_pos > 16) throw std::invalid_argument("peer_exchange: too many fixed bits");
+    // 2 resident CTAs per SM: enough 128-bit requests in flight to cover the NVLink round trip (each thread keeps 8), and
+    // three quarters of every SM stay free for the passes running on the other slices
+    uint64_t blocks = uint64_t(sm_count) * 2;
+    const uint64_t chunks = ((a.count - a.count / 2 + 1023) / 1024) * uint64_t(a.n_peers);
+    if (blocks > chunks) blocks = chunks;
+    if (blocks < 1) blocks = 1;
+    peer_exchange_kernel<<<unsigned(blocks), 256, 0, stream>>>(a);
+    PQB_CUDA_CHECK(cudaGetLastError());
 }
 
 // pack / unpack one sub-block of the shard for a global<->local qubit exchange: the sub-block is the set of amplitudes

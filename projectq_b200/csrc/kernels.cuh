@@ -13,6 +13,13 @@ struct Ctx {
     uint64_t* launches;
 };
 
+// restriction of a launch to a slice of the state: the (ascending) local bits pos[0..n) are held at the values in val
+struct Slice {
+    int n = 0;
+    uint8_t pos[16] = {};
+    uint64_t val = 0;
+};
+
 constexpr int kMaxDense = 5;        // widest dense gate (reference: simulator.hpp:522-523 throws above 5)
 constexpr int kReducePartials = 65536;  // capacity (in doubles) of the partial-sum scratch the reductions use
 
@@ -20,10 +27,10 @@ constexpr int kReducePartials = 65536;  // capacity (in doubles) of the partial-
 // tpos: ascending bit positions of the k targets (matrix bit l <-> tpos[l]); cpos: ascending control positions.
 // m_host: 2^k x 2^k row-major (re,im).
 void apply_dense(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
-                 const double* m_host);
+                 const double* m_host, const Slice& slice = Slice());
 // Diagonal pass: psi[i] *= d[bits of i at tpos] on the control-satisfying subspace; d_host has 2^k (re,im) entries.
 void apply_diagonal(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl,
-                    const uint8_t* cpos, const double* d_host);
+                    const uint8_t* cpos, const double* d_host, const Slice& slice = Slice());
 
 // sum_{(i & mask) == val} |psi_i|^2 -> d_out[0]  (reference: get_probability, simulator.hpp:363-367)
 void norm_masked(const Ctx& c, const double2* psi, uint64_t n_amps, uint64_t mask, uint64_t val, double* d_partials,
@@ -47,8 +54,30 @@ void gather_indices(const Ctx& c, const double2* psi, const uint64_t* d_indices,
 
 // exchange two local index bits of the state in place (n_bits >= 2)
 void swap_local_bits(const Ctx& c, double2* psi, int n_bits, int b0, int b1);
-// exchange over peer-mapped memory: swap mine[bit pos == my_bit][j] with peer[bit pos == 1 - my_bit][j], j in [first, first+count)
-void peer_swap(const Ctx& c, double2* mine, double2* peer, uint64_t first, uint64_t count, int pos, int my_bit);
+// Global<->local remap over peer-mapped memory, one kernel per rank (see kernels.cu).  Sub-block element j of a shard is
+// shard[insert_zero_bits(j, pos) | pattern]; pos = ascending union of the exchanged local bits and the slice bits.
+constexpr int kMaxExchangePeers = 7;   // 2^3 - 1: three rank bits of an 8-GPU box exchanged at once
+constexpr int kFlagArrive = 0;         // sync page: [kFlagArrive + rank] and [kFlagDone + rank], written by that rank
+constexpr int kFlagDone = 64;
+struct ExchangeArgs {
+    double2* mine;                                  // my shard
+    double2* peer[kMaxExchangePeers];               // the peers' shards, mapped into this process
+    uint64_t out_pattern[kMaxExchangePeers];        // my sub-block that trades places with peer p's
+    uint64_t in_pattern;                            // the peers' sub-block that is mine (same bits for every peer)
+    uint64_t count;                                 // amplitudes per sub-block
+    uint8_t lower[kMaxExchangePeers];               // 1: this rank handles the first half of the j range of that pair
+    uint8_t pos[16];
+    int n_peers, n_pos;
+    // cross-GPU ordering (sync = 0: the caller orders the kernels itself, used by single-process tests)
+    int sync, my_rank;
+    int peer_rank[kMaxExchangePeers];
+    unsigned long long epoch[kMaxExchangePeers];    // per-pair exchange counter (same value on both ranks of the pair)
+    unsigned long long* my_flags;                   // my sync page
+    unsigned long long* peer_flags[kMaxExchangePeers];  // the peers' sync pages, mapped
+    unsigned int* block_counter;                    // zero-initialised device word
+    int* host_error;                                // mapped pinned host word: non-zero after a spin timed out
+};
+void peer_exchange(cudaStream_t stream, const ExchangeArgs& a, int sm_count);
 // remap support: gather / scatter the half of the shard whose local bit `pos` equals `value` (piece [first, first+count))
 void pack_half(cudaStream_t stream, const double2* shard, double2* packed, uint64_t first, uint64_t count, int pos, int value);
 void unpack_half(cudaStream_t stream, double2* shard, const double2* packed, uint64_t first, uint64_t count, int pos, int value);

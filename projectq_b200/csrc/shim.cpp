@@ -225,8 +225,12 @@ public:
         check(pqb_collapse_wavefunction(sim_, ids.data(), ids.size(), v.data(), v.size()));
     }
     void run() {
-        py::gil_scoped_release nogil;
-        check(pqb_run(sim_));
+        int st;
+        {
+            py::gil_scoped_release nogil;
+            st = pqb_run(sim_);
+        }
+        check(st);
     }
     py::tuple cheat() {
         size_t n = 0;
@@ -249,8 +253,12 @@ public:
     }
     void apply_gate_stream(const py::bytes& packed, size_t n_gates, bool fuse) {
         std::string s = packed;
-        py::gil_scoped_release nogil;
-        check(pqb_apply_gate_stream(sim_, s.data(), s.size(), n_gates, fuse ? 1 : 0));
+        int st;
+        {
+            py::gil_scoped_release nogil;
+            st = pqb_apply_gate_stream(sim_, s.data(), s.size(), n_gates, fuse ? 1 : 0);
+        }
+        check(st);
     }
     // f1: a whole command list's worth of matrix gates in ONE native call.  gates = list of
     // (matrix, target ids, control ids); matrices are anything NumPy can view as a complex 2^k x 2^k array, so the
@@ -280,8 +288,12 @@ public:
             ++n_gates;
         }
         if (n_gates == 0) return;
-        py::gil_scoped_release nogil;
-        check(pqb_apply_gate_stream(sim_, buf.data(), buf.size(), n_gates, fuse ? 1 : 0));
+        int st;
+        {
+            py::gil_scoped_release nogil;
+            st = pqb_apply_gate_stream(sim_, buf.data(), buf.size(), n_gates, fuse ? 1 : 0);
+        }
+        check(st);
     }
     void init_random_state(uint32_t n, uint64_t seed) { check(pqb_init_random_state(sim_, n, seed)); }
     double norm_squared() {
@@ -290,19 +302,34 @@ public:
         return v;
     }
     void synchronize() {
-        py::gil_scoped_release nogil;
-        check(pqb_synchronize(sim_));
+        int st;
+        {
+            py::gil_scoped_release nogil;
+            st = pqb_synchronize(sim_);
+        }
+        check(st);
     }
     void timer_start() { check(pqb_timer_start(sim_)); }
     double timer_stop() {
         double ms = 0.0;
-        py::gil_scoped_release nogil;
-        check(pqb_timer_stop(sim_, &ms));
+        int st;
+        {
+            py::gil_scoped_release nogil;
+            st = pqb_timer_stop(sim_, &ms);
+        }
+        check(st);
         return ms;
     }
     py::dict stats() {
         pqb_stats s;
-        check(pqb_get_stats(sim_, &s));
+        {
+            int st;
+            {
+                py::gil_scoped_release nogil;
+                st = pqb_get_stats(sim_, &s);
+            }
+            check(st);
+        }
         py::dict d;
         d["kernel_launches"] = s.kernel_launches;
         py::list passes;
@@ -314,15 +341,28 @@ public:
         d["remap_bytes_sent"] = s.remap_bytes_sent;
         d["remap_ms"] = s.remap_ms;
         d["p2p_remaps"] = s.p2p_remaps;
+        d["pipelined_remaps"] = s.pipelined_remaps;
+        d["remap_qubits"] = s.remap_qubits;
+        d["remap_comm_ms"] = s.remap_comm_ms;
+        py::list pass_ms;
+        for (int k = 0; k < 6; ++k) pass_ms.append(s.pass_ms[k]);
+        d["pass_ms"] = pass_ms;
+        d["diag_ms"] = s.diag_ms;
         return d;
     }
     void reset_stats() { check(pqb_reset_stats(sim_)); }
+    void set_profiling(bool on) { check(pqb_set_profiling(sim_, on ? 1 : 0)); }
     void flush_l2(size_t bytes) { check(pqb_flush_l2(sim_, bytes)); }
     double bench_dense_pass(const carray& m, const std::vector<uint32_t>& positions, uint64_t ctrl_mask, int repeats) {
         double ms = 0.0;
         check(pqb_bench_dense_pass(sim_, reinterpret_cast<const double*>(m.data()), positions.data(), positions.size(),
                                    ctrl_mask, repeats, &ms));
         return ms;
+    }
+    void selftest_sliced_pass(const carray& m, const std::vector<uint32_t>& positions, uint64_t ctrl_mask,
+                              uint64_t slice_mask) {
+        check(pqb_selftest_sliced_pass(sim_, reinterpret_cast<const double*>(m.data()), positions.data(), positions.size(),
+                                       ctrl_mask, slice_mask));
     }
     double measure_fp64_peak() {
         double v = 0.0;
@@ -354,6 +394,18 @@ PYBIND11_MODULE(_pqb_shim, m) {
         const int st = pqb_nccl_unique_id(id);
         if (st != PQB_OK) raise(st, pqb_last_error(nullptr));
         return py::bytes(id, 128);
+    });
+    m.def("selftest_exchange", [](int device, int world, int n_local_bits, const std::vector<std::pair<int, int>>& pairs,
+                                  uint64_t slice_mask) {
+        std::vector<int32_t> flat;
+        for (auto& p : pairs) {
+            flat.push_back(p.first);
+            flat.push_back(p.second);
+        }
+        uint64_t bad = 0;
+        const int st = pqb_selftest_exchange(device, world, n_local_bits, flat.data(), pairs.size(), slice_mask, &bad);
+        if (st != PQB_OK) raise(st, pqb_last_error(nullptr));
+        return bad;
     });
     py::class_<Simulator>(m, "Simulator")
         .def(py::init<uint32_t, int, int, int, int, py::object, int>(), py::arg("seed") = 1, py::arg("device") = 0,
@@ -389,8 +441,10 @@ PYBIND11_MODULE(_pqb_shim, m) {
         .def("timer_stop", &Simulator::timer_stop)
         .def("stats", &Simulator::stats)
         .def("reset_stats", &Simulator::reset_stats)
+        .def("set_profiling", &Simulator::set_profiling)
         .def("flush_l2", &Simulator::flush_l2)
         .def("bench_dense_pass", &Simulator::bench_dense_pass)
+        .def("selftest_sliced_pass", &Simulator::selftest_sliced_pass)
         .def("measure_fp64_peak", &Simulator::measure_fp64_peak)
         .def("measure_copy_bandwidth", &Simulator::measure_copy_bandwidth)
         .def("num_qubits", &Simulator::num_qubits);

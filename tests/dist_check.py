@@ -43,6 +43,24 @@ def main():
         return err
 
     rng = np.random.default_rng(99)  # same stream on every rank
+    expect = os.environ.get("PQB_EXPECT", "pipelined")  # which remap path this run must have taken
+
+    # 0. a lazily allocating program: gate on the first qubit right after its allocation, one run() per gate (the default
+    #    gate_fusion=False path) — the first qubits must land on local bits, not on rank bits with nothing to evict
+    gpu, chk = make(5), OracleSimulator(5)
+    for q in range(4):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+        for m, t, c in ((rand_unitary(rng, 1), [q], []), (rand_unitary(rng, 1), [q], [q - 1] if q else [])):
+            gpu.apply_controlled_gate(m, t, c)
+            gpu.run()
+            chk.apply_controlled_gate(m, t, c)
+    m = rand_unitary(rng, 4)
+    gpu.apply_controlled_gate(m, [3, 1, 0, 2], [])
+    chk.apply_controlled_gate(m, [3, 1, 0, 2], [])
+    same(gpu, chk, "lazy allocation")
+    assert list(gpu.measure_qubits([0, 1, 2, 3])) == list(chk.measure_qubits([0, 1, 2, 3]))
+    del gpu
 
     # 1. allocate one by one (the first log2(world) qubits land on rank bits), gates on every qubit -> remaps
     n = 12
@@ -66,6 +84,12 @@ def main():
     same(gpu, chk, "random circuit")
     st = gpu.stats()
     assert st["remaps"] > 0, st
+    if expect == "pipelined":
+        assert st["pipelined_remaps"] > 0 and st["p2p_remaps"] > 0, st
+    elif expect == "p2p":
+        assert st["pipelined_remaps"] == 0 and st["p2p_remaps"] > 0, st
+    elif expect == "nccl":
+        assert st["p2p_remaps"] == 0, st
 
     # 2. queries
     for _ in range(6):
@@ -133,9 +157,9 @@ def main():
     same(gpu, chk, "re-allocate")
     del gpu
 
-    # 6. a wider state: fused brickwork on 20 qubits vs the oracle
+    # 6. a wider state: fused brickwork on 20 qubits vs the oracle (several flushes: the qubits that left come back)
     n = 20
-    gates = brickwork_circuit(n, 3, seed=8)
+    gates = brickwork_circuit(n, 6, seed=8)
     gpu, chk = make(1), OracleSimulator(1)
     wf = rand_state(rng, n)
     for q in range(n):
@@ -143,9 +167,11 @@ def main():
         chk.allocate_qubit(q)
     gpu.set_wavefunction(wf, list(range(n)))
     chk.set_wavefunction(wf, list(range(n)))
-    for m, t, c in gates:
+    for i, (m, t, c) in enumerate(gates):
         gpu.apply_controlled_gate(m, t, c)
         chk.apply_controlled_gate(m, t, c)
+        if i % 97 == 96:
+            gpu.run()
     err = same(gpu, chk, "brickwork 20q")
     st = gpu.stats()
     if rank == 0:

@@ -1,7 +1,7 @@
 """Makes the reference's *Python* package importable (test infrastructure only).
 
 /root/reference is read-only and exists only in the build container; oracle/Makefile stages a copy of the package under
-the git-ignored oracle/_ref/refpkg/, which travels to the GPU box with the other built artefacts, so the drop-in tests
+the git-ignored baseline/_ref/, which travels to the GPU box with the other built artefacts, so the drop-in tests
 (`MainEngine(projectq_b200.Simulator(...))`, the reference's own test-suite on the CUDA backend) can run there.
 ``import projectq`` pulls matplotlib (absent here) through
 backends/_circuits/_plot.py, and ``projectq.backends._sim._simulator`` wants the compiled ``_cppsim``; both are
@@ -14,7 +14,7 @@ import types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 if not os.path.isdir(os.path.join(REF, "projectq")):
-    REF = os.path.join(ROOT, "oracle", "_ref", "refpkg")
+    REF = os.path.join(ROOT, "baseline", "_ref")
 
 
 def available():

@@ -10,7 +10,7 @@ Two switches (environment):
   PQB_ENGINE = ours (default)   `projectq.backends.Simulator` is projectq_b200.Simulator (our engine class)
              = reference        the reference's own Python engine class stays; only the native seam is swapped
 
-The reference package comes from /root/reference in the build container and from the staged copy under oracle/_ref/refpkg/
+The reference package comes from /root/reference in the build container and from the staged copy under baseline/_ref/
 on the GPU box (tests/refenv.py).
 """
 import os

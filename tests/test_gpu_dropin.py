@@ -12,7 +12,7 @@ _simulator_test.py:80-93) is done here with the CUDA backend:
   probabilities / sampled amplitudes within 1e-12;
 * `examples/shor.py`'s `run_shor` itself, with emulated and with fully decomposed modular arithmetic.
 
-The reference's Python package is found by tests/refenv.py (staged under oracle/_ref/refpkg/ by oracle/Makefile).
+The reference's Python package is found by tests/refenv.py (staged under baseline/_ref/ by oracle/Makefile).
 """
 import importlib.util
 import json
@@ -50,14 +50,14 @@ def test_reference_suite_on_cuda(engine):
     """>= 59 of the reference's 60 Simulator/factoring tests pass with CUDA under the engine.  (With the reference's C++
     simulator exactly one fails here — `numpy.array(list, copy=False)` under NumPy 2, _simulator_test.py:562 — and
     cheat() returning an ndarray makes even that one pass.)"""
-    assert refenv.available(), "reference package not staged (oracle/_ref/refpkg): run `make -C oracle` in the build container"
+    assert refenv.available(), "reference package not staged (baseline/_ref): run `make -C oracle` in the build container"
     failed, passed, tail = run_suite(engine)
     assert passed >= 59 and failed <= 1, tail
 
 
 @pytest.fixture(scope="module")
 def pq():
-    assert refenv.available(), "reference package not staged (oracle/_ref/refpkg): run `make -C oracle` in the build container"
+    assert refenv.available(), "reference package not staged (baseline/_ref): run `make -C oracle` in the build container"
     return refenv.import_projectq("cuda")
 
 

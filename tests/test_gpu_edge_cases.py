@@ -239,3 +239,40 @@ def test_id_reuse_and_noncontiguous_ids(Backend):
     gpu.apply_controlled_gate(m, [3, 7], [])
     chk.apply_controlled_gate(marg(chk, m), [3, 7], [])
     same(gpu, chk)
+
+
+def test_sliced_pass_equals_whole_pass(Backend):
+    """a dense pass restricted in turn to every slice of the state (the way the sharded engine runs the passes around a
+    remap) equals one unrestricted pass"""
+    rng = np.random.default_rng(77)
+    n = 16
+    for k, positions, ctrl_mask, slice_mask in [(1, [5], 0, 0b11 << 14), (2, [0, 9], 1 << 3, (1 << 15) | (1 << 1)),
+                                                (4, [2, 3, 8, 11], 0, (1 << 15) | (1 << 14) | (1 << 13)),
+                                                (4, [0, 1, 2, 3], 1 << 7, (1 << 4) | (1 << 12)),
+                                                (3, [0, 1, 2], 0, (1 << 10) | (1 << 9) | (1 << 15)),
+                                                (5, [1, 4, 6, 7, 13], 1 << 0, (1 << 2) | (1 << 15))]:
+        gpu, chk = Backend(1), checker(1)
+        for q in range(n):
+            gpu.allocate_qubit(q)
+            chk.allocate_qubit(q)
+        wf = rand_state(rng, n)
+        gpu.set_wavefunction(wf, list(range(n)))
+        chk.set_wavefunction(warg(chk, wf), list(range(n)))
+        m = rand_unitary(rng, k)
+        gpu.selftest_sliced_pass(m, positions, ctrl_mask, slice_mask)
+        chk.apply_controlled_gate(marg(chk, m), positions, [b for b in range(n) if (ctrl_mask >> b) & 1])
+        chk.run()
+        same(gpu, chk)
+
+
+def test_exchange_kernel_permutation_single_device():
+    """the peer-memory exchange kernel's index arithmetic (sub-block patterns, pair split, slices, 1-3 exchanged bits) on
+    one device: `world` shards in one process, compared with the permutation a global<->local remap must perform"""
+    from projectq_b200.backend import selftest_exchange
+
+    for world, n_local, pairs, slice_mask in [(2, 10, [(0, 9)], 0), (2, 10, [(0, 0)], 0b110), (2, 12, [(0, 5)], (1 << 11) | (1 << 2)),
+                                              (4, 12, [(0, 11), (1, 10)], 0), (4, 12, [(1, 3), (0, 7)], (1 << 9) | (1 << 8) | (1 << 0)),
+                                              (8, 14, [(0, 13), (1, 12), (2, 11)], (1 << 10) | (1 << 9) | (1 << 8)),
+                                              (8, 14, [(2, 4), (0, 6), (1, 13)], 1 << 12), (8, 13, [(1, 12)], 0),
+                                              (4, 4, [(0, 3), (1, 2)], 0b01), (2, 1, [(0, 0)], 0)]:
+        assert selftest_exchange(0, world, n_local, pairs, slice_mask) == 0, (world, n_local, pairs, slice_mask)
