@@ -1114,9 +1114,64 @@ void Engine::emulate_math(int mode, int64_t a, int64_t N, const uint64_t* table,
             active = false;
     }
     if (!active) return;  // this rank's control bits are not all set: identity on the whole shard
+    const size_t bytes = local_amps() * sizeof(double2);
+    if (flat <= size_t(k::kMathGatherBits)) {
+        // Gather through the inverse map (kernels.cuh): tabulate v -> f(v) on the concatenated register value with the
+        // reference's arithmetic (per register: x + a, (x + a) % N, (x * a) % N in C semantics, low bits of the result,
+        // simulator.hpp:255-290 — in 64 bits), then list for every destination value its sources in
+        // ascending order.  A bijection gives one source per destination and the kernel is a pure permutation (bit-exact);
+        // inputs outside a gate's domain (x >= N) collide and are summed, as in the reference.
+        const size_t V = size_t(1) << flat;
+        std::vector<uint32_t> fwd(V);
+        for (size_t v = 0; v < V; ++v) {
+            if (mode == k::MATH_TABLE) {
+                fwd[v] = uint32_t(table[v] & (V - 1));
+                continue;
+            }
+            uint64_t y_all = 0;
+            for (size_t r = 0; r < n_regs; ++r) {
+                const int off = d.reg_off[r], nb = d.reg_off[r + 1] - d.reg_off[r];
+                const long long x = (long long)((v >> off) & ((uint64_t(1) << nb) - 1));
+                long long y;
+                if (mode == k::MATH_ADD)
+                    y = x + a;
+                else if (mode == k::MATH_ADD_MOD)
+                    y = (x + a) % N;
+                else
+                    y = (x * a) % N;
+                y_all |= (uint64_t(y) & ((uint64_t(1) << nb) - 1)) << off;
+            }
+            fwd[v] = uint32_t(y_all);
+        }
+        std::vector<uint32_t> csr(2 * V + 1, 0);  // offsets (V + 1), then sources (V)
+        uint32_t* off = csr.data();
+        uint32_t* src = csr.data() + V + 1;
+        for (size_t v = 0; v < V; ++v) ++off[fwd[v] + 1];
+        for (size_t y = 0; y < V; ++y) off[y + 1] += off[y];
+        {
+            std::vector<uint32_t> fill(off, off + V);
+            for (size_t v = 0; v < V; ++v) src[fill[fwd[v]]++] = uint32_t(v);
+        }
+        k::MathGatherDesc g{};
+        const uint32_t* d_csr = static_cast<const uint32_t*>(small_upload(csr.data(), csr.size() * sizeof(uint32_t)));
+        g.d_inv_off = d_csr;
+        g.d_inv_src = d_csr + V + 1;
+        g.ctrl_mask = d.ctrl_mask;
+        // runs of consecutive positions
+        for (size_t i = 0; i < flat;) {
+            size_t j = i + 1;
+            while (j < flat && d.reg_pos[j] == d.reg_pos[j - 1] + 1) ++j;
+            g.seg[g.n_segs++] = {d.reg_pos[i], uint8_t(j - i), uint8_t(i)};
+            i = j;
+        }
+        for (size_t i = 0; i < flat; ++i) g.reg_mask |= uint64_t(1) << d.reg_pos[i];
+        ensure_scratch(*scratch1_, bytes);
+        k::emulate_math_gather(ctx(), psi(), scratch1_->amps(), local_amps(), g);
+        std::swap(state_, scratch1_);
+        return;
+    }
     if (mode == k::MATH_TABLE)
         d.d_table = static_cast<const unsigned long long*>(small_upload(table, table_len * sizeof(uint64_t)));
-    const size_t bytes = local_amps() * sizeof(double2);
     ensure_scratch(*scratch1_, bytes);
     PQB_CHECK(cudaMemsetAsync(scratch1_->ptr(), 0, bytes, stream_));
     k::emulate_math(ctx(), psi(), scratch1_->amps(), local_amps(), d);

@@ -937,6 +937,42 @@ void emulate_math(const Ctx& c, const double2* in, double2* out, uint64_t n_amps
     launched(c);
 }
 
+__global__ void __launch_bounds__(256) emulate_math_gather_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                                                                  uint64_t n_amps, const __grid_constant__ MathGatherDesc d) {
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n_amps; j += step) {
+        double2 acc = make_double2(0.0, 0.0);
+        if ((j & d.ctrl_mask) != d.ctrl_mask) {
+            const double2 a = in[j];
+            acc.x += a.x;  // 0 + x, like the reference's += onto a zeroed vector (simulator.hpp:264)
+            acc.y += a.y;
+        } else {
+            uint32_t y = 0;
+            for (int s = 0; s < d.n_segs; ++s)
+                y |= uint32_t((j >> d.seg[s].pos) & ((uint64_t(1) << d.seg[s].len) - 1)) << d.seg[s].shift;
+            const uint32_t b = __ldg(d.d_inv_off + y), e = __ldg(d.d_inv_off + y + 1);
+            const uint64_t rest = j & ~d.reg_mask;
+            for (uint32_t q = b; q < e; ++q) {
+                const uint32_t x = __ldg(d.d_inv_src + q);
+                uint64_t src = rest;
+                for (int s = 0; s < d.n_segs; ++s)
+                    src |= uint64_t((x >> d.seg[s].shift) & ((uint32_t(1) << d.seg[s].len) - 1)) << d.seg[s].pos;
+                const double2 a = in[src];
+                acc.x += a.x;
+                acc.y += a.y;
+            }
+        }
+        out[j] = acc;
+    }
+}
+
+void emulate_math_gather(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const MathGatherDesc& d) {
+    uint64_t blocks = (n_amps + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    emulate_math_gather_kernel<<<unsigned(blocks), 256, 0, c.stream>>>(in, out, n_amps, d);
+    launched(c);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Pauli-string operators
 // ------------------------------------------------------------------------------------------------------------------
@@ -1052,6 +1088,123 @@ void pauli_apply(const Ctx& c, const double2* in, double2* out, uint64_t n_amps,
         final_sum_kernel<<<1, 256, 0, c.stream>>>(d_partials, grid, d_norm, 0);
         launched(c);
     }
+}
+
+// ---- tiled Pauli operators --------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
+                                                             double2* __restrict__ acc,
+                                                             const __grid_constant__ PauliTileArgs a,
+                                                             double* __restrict__ partials) {
+    extern __shared__ double2 tile[];
+    const int tile_amps = 1 << a.T;
+    const uint32_t lo_mask = (1u << a.T_lo) - 1;
+    double red = 0.0;
+    for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x) {
+        const uint64_t base = insert_zero_bits(tid_tile, a.tile_pos, a.T);
+        __syncthreads();  // the previous tile is no longer needed
+        for (int t = threadIdx.x; t < tile_amps; t += THREADS) {
+            const uint64_t g = base | (t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
+            tile[t] = in[g];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < tile_amps; t += THREADS) {
+            const uint64_t g = base | (t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
+            double re = 0.0, im = 0.0;
+            for (int k = 0; k < a.n_terms; ++k) {
+                const double2 v = tile[t ^ a.xl[k]];
+                double cr = a.t[k].cre, ci = a.t[k].cim;
+                if (__popcll((g ^ a.t[k].xmask) & a.t[k].zmask) & 1) {
+                    cr = -cr;
+                    ci = -ci;
+                }
+                re = fma(cr, v.x, re);
+                re = fma(-ci, v.y, re);
+                im = fma(cr, v.y, im);
+                im = fma(ci, v.x, im);
+            }
+            if (a.expectation) {
+                const double2 p = tile[t];
+                red += p.x * re + p.y * im;  // Re(conj(psi_j) s_j)
+                continue;
+            }
+            if (!a.first) {
+                const double2 prev = u[g];
+                re += prev.x;
+                im += prev.y;
+            }
+            if (!a.final) {
+                u[g] = make_double2(re, im);
+                continue;
+            }
+            const double ore = re * a.sre - im * a.sim, oim = re * a.sim + im * a.sre;
+            u[g] = make_double2(ore, oim);
+            if (acc != nullptr && (g & a.cmask) == a.cmask) {
+                const double2 o = acc[g];
+                acc[g] = make_double2(o.x + ore, o.y + oim);
+                red += ore * ore + oim * oim;
+            }
+        }
+    }
+    if (partials != nullptr) {
+        red = block_sum(red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = red;
+    }
+}
+
+int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs& a, double* d_partials) {
+    if (a.T > 12 || a.T < 0 || a.n_terms > kTileTerms) throw std::invalid_argument("pauli_tile_pass: bad arguments");
+    constexpr int THREADS = 256;
+    const size_t smem = sizeof(double2) << a.T;
+    static bool configured = false;
+    if (!configured) {
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        configured = true;
+    }
+    uint64_t grid = a.n_tiles;
+    if (grid > 148 * 6) grid = 148 * 6;  // 6 resident 32 KB tiles per SM
+    const bool reduce = a.expectation || (a.final && acc != nullptr);
+    pauli_tile_kernel<THREADS><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+    launched(c);
+    return int(grid);
+}
+
+void reduce_partials(const Ctx& c, const double* d_partials, int n, double* d_out, bool accumulate) {
+    final_sum_kernel<<<1, 256, 0, c.stream>>>(d_partials, n, d_out, accumulate ? 1 : 0);
+    launched(c);
+}
+
+__global__ void __launch_bounds__(256) pauli_gather_accumulate_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                                                                      uint64_t n_amps, const PauliTerm* __restrict__ terms,
+                                                                      int n_terms, int first) {
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n_amps; j += step) {
+        double re = 0.0, im = 0.0;
+        for (int t = 0; t < n_terms; ++t) {
+            const uint64_t s = j ^ __ldg(&terms[t].xmask);
+            const double2 v = in[s];
+            double cr = __ldg(&terms[t].cre), ci = __ldg(&terms[t].cim);
+            if (__popcll(s & __ldg(&terms[t].zmask)) & 1) {
+                cr = -cr;
+                ci = -ci;
+            }
+            re += cr * v.x - ci * v.y;
+            im += cr * v.y + ci * v.x;
+        }
+        if (!first) {
+            const double2 prev = out[j];
+            re += prev.x;
+            im += prev.y;
+        }
+        out[j] = make_double2(re, im);
+    }
+}
+
+void pauli_gather_accumulate(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const PauliTerm* d_terms,
+                             int n_terms, bool first) {
+    const int grid = reduce_grid(n_amps, 256 * 4);
+    pauli_gather_accumulate_kernel<<<grid, 256, 0, c.stream>>>(in, out, n_amps, d_terms, n_terms, first ? 1 : 0);
+    launched(c);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

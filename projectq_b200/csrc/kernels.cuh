@@ -107,6 +107,22 @@ struct MathDesc {
 };
 void emulate_math(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const MathDesc& d);
 
+// The same operation as a gather through the inverse map, for registers of up to kMathGatherBits bits in total: the host
+// tabulates the map v -> f(v) on the concatenated register value once and inverts it into a CSR list (sources of every
+// destination value, ascending), and every output amplitude sums its sources with plain loads and one plain store — no
+// memset of the destination, no atomics, 32 B/amplitude.  Register bits are described as runs of consecutive positions.
+constexpr int kMathGatherBits = 20;
+struct MathGatherDesc {
+    const uint32_t* d_inv_off;  // 2^bits + 1 offsets into d_inv_src
+    const uint32_t* d_inv_src;  // 2^bits source values, grouped by destination value
+    uint64_t ctrl_mask, reg_mask;
+    int n_segs;
+    struct Seg {
+        uint8_t pos, len, shift;  // bits [pos, pos+len) of the index <-> bits [shift, shift+len) of the register value
+    } seg[64];
+};
+void emulate_math_gather(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const MathGatherDesc& d);
+
 // Pauli strings in physical-bit form: (P psi)[j] = phase * (-1)^{popcount(s & zmask)} psi[s], s = j ^ xmask, with
 // phase = coefficient * i^{nY} (reference: apply_term, simulator.hpp:538-550).
 struct PauliTerm {
@@ -121,6 +137,34 @@ void pauli_expectation_group(const Ctx& c, const double2* psi, int n_bits, uint6
 // d_terms must be sorted by xmask.  rank_bits/sign handling of global bits is the caller's business.
 void pauli_apply(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const PauliTerm* d_terms, int n_terms,
                  double scale_re, double scale_im, double2* acc, uint64_t ctrl_mask, double* d_partials, double* d_norm);
+// Tiled form of the same operators (reference: apply_qubit_operator / get_expectation_value / the Taylor loop of
+// emulate_time_evolution, simulator.hpp:292-350,386-438).  A tile is the set of 2^T amplitudes that differ only in the T
+// "tile bits"; a CTA stages one tile in shared memory (one coalesced read of `in`), and every term whose X/Y support lies
+// inside the tile bits finds its partner amplitude psi[j ^ xmask] in shared memory instead of in HBM.  The host covers the
+// X-supports of an operator with a few tile-bit sets (one launch each), so a Taylor order costs a few sweeps instead of one
+// gather stream per distinct xmask.
+constexpr int kTileBits = 11;       // 2^11 amplitudes = 32 KB of shared memory per CTA
+constexpr int kTileTerms = 64;      // terms per launch
+struct PauliTileArgs {
+    PauliTerm t[kTileTerms];
+    uint32_t xl[kTileTerms];        // xmask of each term in tile coordinates
+    int n_terms;
+    int T, T_lo;                    // tile bits; the lowest T_lo of them are the index bits 0..T_lo-1
+    uint8_t tile_pos[16];           // ascending
+    uint64_t n_tiles;
+    // what to do with s_j = sum_t c_t (P_t in)_j:
+    int first;                      // 1: no partial sum in `u` yet;  0: u_j already holds the sum of earlier launches
+    int final;                      // 1: u_j <- scale * (partial + s_j), then the optional accumulation below;  0: u_j <- partial + s_j
+    int expectation;                // 1: only sum_j Re(conj(in_j) s_j) is wanted (u, acc unused)
+    double sre, sim;                // scale
+    uint64_t cmask;                 // acc_j += u_j and norm += |u_j|^2 where (j & cmask) == cmask (final only, acc != nullptr)
+};
+// d_partials receives one double per CTA when `expectation` or (final && acc); grid size is returned
+int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs& a, double* d_partials);
+void reduce_partials(const Ctx& c, const double* d_partials, int n, double* d_out, bool accumulate);
+// out[j] (+)= sum_t c_t (P_t in)[j] by per-term gathers from global memory (terms whose X support no tile covers)
+void pauli_gather_accumulate(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const PauliTerm* d_terms,
+                             int n_terms, bool first);
 // psi_i *= (re,im) where (i & ctrl_mask) == ctrl_mask
 void scale_masked(const Ctx& c, double2* psi, uint64_t n_amps, uint64_t ctrl_mask, double re, double im);
 
