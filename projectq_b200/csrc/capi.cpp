@@ -473,9 +473,10 @@ int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, 
         for (uint32_t f = 0; f < flushes; ++f) {
             for (auto& g : gates) fuser.push(g);
             const pqb::InteractionGraph adj = pqb::interaction_graph(fuser);
-            while (fuser.pending() > 0) {
-                auto passes = fuser.drain_unblocked(max_qubits <= 0 ? 4 : max_qubits, key, blocked);
-                for (auto& ps : passes) {
+            pqb::ShardPlan plan(fuser, max_qubits <= 0 ? 4 : max_qubits);
+            while (true) {
+                for (size_t ci : plan.take_runnable(map, loc)) {
+                    const pqb::FusedPass ps = fuser.fuse_cluster(plan.cluster(ci), key);
                     const uint32_t k = uint32_t(ps.targets.size()), nc = uint32_t(ps.ctrls.size());
                     for (auto t : ps.targets)
                         if (loc[map.at(t)] >= 64) throw std::logic_error("scheduled a pass with an off-device target");
@@ -485,8 +486,8 @@ int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, 
                     put(ps.ctrls.data(), 4 * nc);
                     put(ps.m.data(), 16 * (size_t(1) << k) * (size_t(1) << k));
                 }
-                if (fuser.pending() == 0) break;
-                pqb::RemapChoice choice = pqb::choose_remap(fuser, map, loc, adj);
+                if (plan.finished()) break;
+                pqb::RemapChoice choice = plan.choose(map, loc, adj);
                 std::vector<uint8_t> before = loc;
                 auto swaps = pqb::plan_remap(loc, L, choice.need, &choice.victims);
                 if (swaps.empty()) throw std::logic_error("stuck without a remap");
@@ -502,6 +503,7 @@ int pqb_host_shard_schedule(const void* packed, size_t n_bytes, size_t n_gates, 
                     put32(ev);
                 }
             }
+            fuser.clear();
             put32(0xFFFFFFFEu);
             put32(0);
         }

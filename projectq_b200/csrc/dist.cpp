@@ -114,7 +114,7 @@ InteractionGraph interaction_graph(const Fuser& fuser) {
 }
 
 RemapChoice choose_remap(const Fuser& fuser, const std::map<uint32_t, uint32_t>& map, const std::vector<uint8_t>& loc,
-                         const InteractionGraph& adj) {
+                         const InteractionGraph& adj, bool controls_needed) {
     RemapChoice out;
     std::vector<uint32_t>& need = out.need;
     auto is_local = [&](uint32_t lp) { return loc[lp] < 64; };
@@ -122,7 +122,8 @@ RemapChoice choose_remap(const Fuser& fuser, const std::map<uint32_t, uint32_t>&
     // the oldest waiting gate has no unfinished predecessor, so it waits for one of its own qubits
     const Gate& g = fuser.pending_gate(0);
     for (auto t : g.targets) need.push_back(map.at(t));
-    for (auto c : g.ctrls) need.push_back(map.at(c));
+    if (controls_needed)
+        for (auto c : g.ctrls) need.push_back(map.at(c));
     // While an exchange is being paid for, bring in the other rank-bit qubits too if they are needed sooner than the local
     // qubits they would replace (plain Belady order for this decision).
     {
@@ -210,6 +211,52 @@ RemapChoice choose_remap(const Fuser& fuser, const std::map<uint32_t, uint32_t>&
         off_device.insert(cands[best].id);
     }
     return out;
+}
+
+ShardPlan::ShardPlan(const Fuser& fuser, int max_qubits) : clusters_(fuser.schedule(max_qubits)) {
+    executed_.assign(clusters_.size(), 0);
+    n_left_ = clusters_.size();
+}
+
+std::vector<size_t> ShardPlan::take_runnable(const std::map<uint32_t, uint32_t>& map, const std::vector<uint8_t>& loc) {
+    std::vector<size_t> out;
+    std::set<uint32_t> busy;  // qubits of passes that have to wait: whatever touches them later waits too
+    for (size_t i = 0; i < clusters_.size(); ++i) {
+        if (executed_[i]) continue;
+        const Cluster& cl = clusters_[i];
+        bool ready = true, local = true;
+        for (auto q : cl.targets) {
+            if (busy.count(q)) ready = false;
+            if (loc[map.at(q)] >= 64) local = false;
+        }
+        for (auto q : cl.ctrls)
+            if (busy.count(q)) ready = false;  // a control on a rank bit is fine: it switches whole ranks on or off
+        if (ready && local) {
+            executed_[i] = 1;
+            --n_left_;
+            out.push_back(i);
+        } else {
+            busy.insert(cl.targets.begin(), cl.targets.end());
+            busy.insert(cl.ctrls.begin(), cl.ctrls.end());
+        }
+    }
+    return out;
+}
+
+RemapChoice ShardPlan::choose(const std::map<uint32_t, uint32_t>& map, const std::vector<uint8_t>& loc,
+                              const InteractionGraph& adj) const {
+    // the waiting passes, in order, in the role of gates: the oldest one has no unfinished predecessor, so it waits for one
+    // of its own qubits, and next_use() is the position of the next waiting pass that touches a qubit
+    Fuser waiting;
+    for (size_t i = 0; i < clusters_.size(); ++i) {
+        if (executed_[i]) continue;
+        Gate g;
+        g.targets = clusters_[i].targets;
+        // common controls may stay on rank bits: they are not asked for, but they do count as uses
+        g.ctrls = clusters_[i].ctrls;
+        waiting.push(std::move(g));
+    }
+    return choose_remap(waiting, map, loc, adj, /*controls_needed=*/false);
 }
 
 std::vector<ExchangePeer> plan_exchange(int rank, const std::vector<std::pair<int, int>>& swaps) {

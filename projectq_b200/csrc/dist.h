@@ -42,7 +42,30 @@ struct RemapChoice {
 // first (Belady); ties (not needed again in this flush) go to a qubit that shares gates with a qubit already off-device,
 // then to the one with the fewest interaction partners, then to the highest bit.
 RemapChoice choose_remap(const Fuser& fuser, const std::map<uint32_t, uint32_t>& id_to_logical,
-                         const std::vector<uint8_t>& loc, const InteractionGraph& adj);
+                         const std::vector<uint8_t>& loc, const InteractionGraph& adj, bool controls_needed = true);
+
+// One flush of a sharded run, scheduled at PASS level.  The whole pending stream is scheduled once, exactly as on one GPU,
+// so the number of fused passes does not depend on the sharding (scheduling gate by gate around the off-device qubits cost
+// 2-4 extra passes per flush on the brickwork benchmark: the passes next to a remap came out half empty).  The passes are
+// then executed in an order that respects their dependencies: everything whose target qubits are on-device runs before a
+// remap is paid for, and the remap is chosen like before (choose_remap) with passes in the role of gates.
+class ShardPlan {
+public:
+    ShardPlan(const Fuser& fuser, int max_qubits);
+    bool finished() const { return n_left_ == 0; }
+    size_t size() const { return clusters_.size(); }
+    const Cluster& cluster(size_t i) const { return clusters_[i]; }
+    // the passes that can run now (targets on local bits, all predecessors executed), in execution order; marks them executed
+    std::vector<size_t> take_runnable(const std::map<uint32_t, uint32_t>& id_to_logical, const std::vector<uint8_t>& loc);
+    // nothing is runnable: which qubits to bring on-device and whom to evict
+    RemapChoice choose(const std::map<uint32_t, uint32_t>& id_to_logical, const std::vector<uint8_t>& loc,
+                       const InteractionGraph& adj) const;
+
+private:
+    std::vector<Cluster> clusters_;
+    std::vector<char> executed_;
+    size_t n_left_ = 0;
+};
 
 // Who exchanges what in a (multi-bit) remap.  Exchanging rank bits r_i with local bits b_i sends, from every rank, the
 // sub-block whose local bits (b_i) spell beta to the rank whose bits (r_i) spell beta, and the sub-block that arrives from

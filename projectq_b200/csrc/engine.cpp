@@ -654,34 +654,24 @@ bool Engine::leaves_from_low_bit(int b, size_t n_swaps) const {
     return dist_->p2p_enabled() ? b < 3 : b < L_ - int(n_swaps);
 }
 
-void Engine::resolve_phase(int width, std::vector<Launch>& out, bool eager, size_t hold) {
-    auto key = [this](uint32_t id) -> uint64_t {
-        auto it = map_.find(id);
-        if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
-        return loc_[it->second];
-    };
-    auto blocked = [this](uint32_t id) -> bool {
-        auto it = map_.find(id);
-        if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
-        return loc_[it->second] >= 64;
-    };
-    std::vector<char> done;
-    const std::vector<Cluster> clusters = fuser_.schedule_unblocked(width, blocked, done);
-    for (size_t c = 0; c < clusters.size(); ++c) {
-        Launch l = resolve_pass(fuser_.fuse_cluster(clusters[c], key));
-        if (eager && out.empty() && c + hold < clusters.size())
+void Engine::resolve_phase(ShardPlan& plan, std::vector<Launch>& out, bool eager, size_t hold) {
+    auto key = [this](uint32_t id) -> uint64_t { return loc_[map_.at(id)]; };
+    const std::vector<size_t> runnable = plan.take_runnable(map_, loc_);
+    for (size_t c = 0; c < runnable.size(); ++c) {
+        Launch l = resolve_pass(fuser_.fuse_cluster(plan.cluster(runnable[c]), key));
+        if (eager && out.empty() && c + hold < runnable.size())
             launch(l);  // the GPU works on this pass while the host multiplies the matrices of the next one
         else
             out.push_back(std::move(l));
     }
-    fuser_.remove_done(done);
 }
 
-// Sharded run(): execute everything that touches only on-device qubits, and only then pay for a remap.  The remap brings
-// in the rank-bit qubits of the oldest waiting gate and evicts the local qubits that are needed last (Belady), so a
-// brickwork circuit needs about one remap per flush instead of one per layer.  The remap itself moves all its qubits in
-// one peer-memory exchange and is pipelined slice by slice against the last passes before it and the first passes after
-// it (pipelined_exchange), so that NVLink traffic and HBM-bound passes run at the same time.
+// Sharded run().  The flush is scheduled into passes once, exactly as on one GPU (ShardPlan), and every pass whose targets
+// are on-device runs before a remap is paid for.  The remap brings in the rank-bit qubits of the oldest waiting pass and
+// evicts the local qubits that are needed last (Belady), so a brickwork circuit needs one remap per flush instead of one
+// per layer.  The remap itself moves all its qubits in one peer-memory exchange and is pipelined slice by slice against the
+// last passes before it and the first passes after it (pipelined_exchange), so that NVLink traffic and HBM-bound passes
+// run at the same time.
 void Engine::run_sharded() {
     static const int max_slice_bits = [] {
         const char* e = getenv("PQB_REMAP_SLICE_BITS");  // 0 switches the pipeline off
@@ -689,12 +679,19 @@ void Engine::run_sharded() {
     }();
     constexpr size_t kTail = 3, kHead = 4;  // passes before / after the remap that may run slice by slice
     const int width = fusion_max_ > 0 ? fusion_max_ : 4;
-    const InteractionGraph adj = interaction_graph(fuser_);  // of this flush: breaks ties between eviction candidates
     try {
+        // every id must be known before anything is applied (the reference would silently insert into map_)
+        for (size_t gi = 0; gi < fuser_.pending(); ++gi) {
+            const Gate& gt = fuser_.pending_gate(gi);
+            for (auto t : gt.targets) pos_of(t, "apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
+            for (auto c : gt.ctrls) pos_of(c, "apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
+        }
+        const InteractionGraph adj = interaction_graph(fuser_);  // of this flush: breaks ties between eviction candidates
+        ShardPlan plan(fuser_, width);
         std::vector<Launch> held;  // resolved but not yet launched (the candidates for a pipeline's tail)
-        resolve_phase(width, held, true, kTail);
-        while (fuser_.pending() > 0) {
-            const RemapChoice choice = choose_remap(fuser_, map_, loc_, adj);
+        resolve_phase(plan, held, true, kTail);
+        while (!plan.finished()) {
+            const RemapChoice choice = plan.choose(map_, loc_, adj);
             // plan on a copy of the layout first: a remap that needs a local pre-pass is not pipelined
             std::vector<uint8_t> planned = loc_;
             std::vector<std::pair<int, int>> swaps;
@@ -721,7 +718,7 @@ void Engine::run_sharded() {
                 for (auto& l : held) launch(l);
                 held.clear();
                 make_local(choice.need, &choice.victims);
-                resolve_phase(width, held, true, kTail);
+                resolve_phase(plan, held, true, kTail);
                 continue;
             }
             loc_ = planned;
@@ -746,7 +743,7 @@ void Engine::run_sharded() {
             held.clear();
             // what can run once the exchanged qubits are on-device; resolved while the GPU works through the launches above
             std::vector<Launch> next;
-            resolve_phase(width, next, false, 0);
+            resolve_phase(plan, next, false, 0);
             size_t n_head = 0;
             while (n_head < next.size() && n_head < kHead) {
                 const uint64_t u = used | next[n_head].touched();
@@ -771,6 +768,7 @@ void Engine::run_sharded() {
             }
         }
         for (auto& l : held) launch(l);
+        fuser_.clear();
     } catch (...) {
         fuser_.clear();
         throw;
@@ -1254,6 +1252,98 @@ static void to_physical(std::vector<k::PauliTerm>& terms, const std::vector<uint
     }
 }
 
+// ---- tiled execution of a Pauli-string operator (kernels.cuh pauli_tile_pass) -------------------------------------------
+// Cover the X/Y supports of the terms with sets of tile bits.  Every set holds index bits 0 and 1 (so that a tile is read
+// in runs of at least 64 bytes) plus the bits that the most still-uncovered terms need; a term is applied by the first
+// launch whose tile bits contain its whole xmask (z factors are signs and never need a partner amplitude).  Terms whose
+// support is too large for any tile are returned in `wide` and go through per-term global gathers.
+struct PauliPlan {
+    std::vector<k::PauliTileArgs> launches;  // in execution order; first/final/scale are filled in by the caller
+    std::vector<k::PauliTerm> wide;
+};
+
+static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
+    PauliPlan plan;
+    const int T = std::min(k::kTileBits, L);
+    const uint64_t low2 = L >= 2 ? 3 : (L == 1 ? 1 : 0);
+    std::vector<int> todo;
+    for (size_t i = 0; i < terms.size(); ++i) {
+        if (__builtin_popcountll(terms[i].xmask | low2) > T)
+            plan.wide.push_back(terms[i]);
+        else
+            todo.push_back(int(i));
+    }
+    auto emit = [&](uint64_t S, const std::vector<int>& members) {
+        // fill up with the lowest unused bits: a full-size tile keeps the loads long and the grid the same for every launch
+        for (int b = 0; b < L && __builtin_popcountll(S) < T; ++b) S |= uint64_t(1) << b;
+        k::PauliTileArgs base{};
+        base.T = T;
+        int n = 0;
+        for (int b = 0; b < L; ++b)
+            if ((S >> b) & 1) base.tile_pos[n++] = uint8_t(b);
+        base.T_lo = 0;
+        while (base.T_lo < T && base.tile_pos[base.T_lo] == base.T_lo) ++base.T_lo;
+        base.n_tiles = uint64_t(1) << (L - T);
+        size_t at = 0;
+        do {
+            k::PauliTileArgs a = base;
+            for (; at < members.size() && a.n_terms < k::kTileTerms; ++at) {
+                const k::PauliTerm& tm = terms[members[at]];
+                a.t[a.n_terms] = tm;
+                a.xl[a.n_terms] = uint32_t(extract_bits(tm.xmask, base.tile_pos, T));
+                ++a.n_terms;
+            }
+            plan.launches.push_back(a);
+        } while (at < members.size());
+    };
+    while (!todo.empty()) {
+        uint64_t S = low2 | terms[todo[0]].xmask;  // the oldest uncovered term always fits: progress is guaranteed
+        while (__builtin_popcountll(S) < T) {
+            int count[64] = {0};
+            for (int i : todo) {
+                const uint64_t extra = terms[i].xmask & ~S;
+                if (extra == 0 || __builtin_popcountll(S | terms[i].xmask) > T) continue;
+                for (uint64_t m = extra; m; m &= m - 1) ++count[__builtin_ctzll(m)];
+            }
+            int best = -1;
+            for (int b = 0; b < L; ++b)
+                if (count[b] > 0 && (best < 0 || count[b] > count[best])) best = b;
+            if (best < 0) break;
+            S |= uint64_t(1) << best;
+        }
+        std::vector<int> members, rest;
+        for (int i : todo) ((terms[i].xmask & ~S) == 0 ? members : rest).push_back(i);
+        emit(S, members);
+        todo.swap(rest);
+    }
+    if (plan.launches.empty()) emit(low2, {});  // no tile-able term: an empty launch still finalises (scale / accumulate)
+    return plan;
+}
+
+// u <- scale * sum_t c_t P_t in   (and optionally acc += u on the control subspace with |u|^2 summed into d_norm)
+void Engine::run_pauli_plan(PauliPlan& plan, const double2* in, double2* u, double sre, double sim, double2* acc, uint64_t cmask,
+                            double* d_norm) {
+    bool first = true;
+    if (!plan.wide.empty()) {
+        const k::PauliTerm* d_terms =
+            static_cast<const k::PauliTerm*>(small_upload(plan.wide.data(), plan.wide.size() * sizeof(k::PauliTerm)));
+        k::pauli_gather_accumulate(ctx(), in, u, local_amps(), d_terms, int(plan.wide.size()), true);
+        first = false;
+    }
+    for (size_t i = 0; i < plan.launches.size(); ++i) {
+        k::PauliTileArgs& a = plan.launches[i];
+        a.first = first ? 1 : 0;
+        a.final = i + 1 == plan.launches.size() ? 1 : 0;
+        a.expectation = 0;
+        a.sre = sre;
+        a.sim = sim;
+        a.cmask = cmask;
+        const int grid = k::pauli_tile_pass(ctx(), in, u, a.final ? acc : nullptr, a, d_partials_);
+        if (a.final && acc != nullptr && d_norm != nullptr) k::reduce_partials(ctx(), d_partials_, grid, d_norm, false);
+        first = false;
+    }
+}
+
 double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, size_t n_ids) {
     run();
     auto all_terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);  // logical masks
@@ -1287,11 +1377,20 @@ double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, si
         std::stable_sort(batch.begin(), batch.end(),
                          [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
         const bool active = !dist_ || (uint64_t(rank_) & dist_->free_rank_bits_mask()) == 0;
+        if (!active) continue;
+        // tile-able terms: one read of the state per tile-bit set; the rest: one pair sweep per distinct xmask
+        PauliPlan plan = plan_pauli_tiles(batch, L_);
+        for (auto& a : plan.launches) {
+            if (a.n_terms == 0) continue;
+            a.expectation = 1;
+            const int grid = k::pauli_tile_pass(ctx(), psi(), nullptr, nullptr, a, d_partials_);
+            k::reduce_partials(ctx(), d_partials_, grid, d_acc, true);
+        }
         size_t i = 0;
-        while (active && i < batch.size()) {
+        while (i < plan.wide.size()) {
             size_t j = i;
-            while (j < batch.size() && batch[j].xmask == batch[i].xmask && j - i < 64) ++j;
-            k::pauli_expectation_group(ctx(), psi(), L_, batch[i].xmask, &batch[i], int(j - i), d_partials_, d_acc);
+            while (j < plan.wide.size() && plan.wide[j].xmask == plan.wide[i].xmask && j - i < 64) ++j;
+            k::pauli_expectation_group(ctx(), psi(), L_, plan.wide[i].xmask, &plan.wide[i], int(j - i), d_partials_, d_acc);
             i = j;
         }
     }
@@ -1321,11 +1420,8 @@ void Engine::apply_qubit_operator(const TermsView& t, const uint32_t* ids, size_
                      [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
     const size_t bytes = local_amps() * sizeof(double2);
     ensure_scratch(*scratch1_, bytes);
-    const k::PauliTerm* d_terms =
-        terms.empty() ? nullptr
-                      : static_cast<const k::PauliTerm*>(small_upload(terms.data(), terms.size() * sizeof(k::PauliTerm)));
-    k::pauli_apply(ctx(), psi(), scratch1_->amps(), local_amps(), d_terms, int(terms.size()), 1.0, 0.0, nullptr, 0, nullptr,
-                   nullptr);
+    PauliPlan plan = plan_pauli_tiles(terms, L_);
+    run_pauli_plan(plan, psi(), scratch1_->amps(), 1.0, 0.0, nullptr, 0, nullptr);
     std::swap(state_, scratch1_);
 }
 
@@ -1356,9 +1452,7 @@ void Engine::emulate_time_evolution(const TermsView& t, double time, const uint3
     const size_t bytes = local_amps() * sizeof(double2);
     ensure_scratch(*scratch1_, bytes);
     ensure_scratch(*scratch2_, bytes);
-    const k::PauliTerm* d_terms =
-        terms.empty() ? nullptr
-                      : static_cast<const k::PauliTerm*>(small_upload(terms.data(), terms.size() * sizeof(k::PauliTerm)));
+    PauliPlan plan = plan_pauli_tiles(terms, L_);
     double* d_norm = d_scalars_;
     for (unsigned i = 0; i < s; ++i) {
         double2* v = scratch1_->amps();
@@ -1369,11 +1463,10 @@ void Engine::emulate_time_evolution(const TermsView& t, double time, const uint3
             // coeff = (-time * I) / (s * (k + 1))
             const double cim = -time / double(s * (kk + 1));
             if (active) {
-                k::pauli_apply(ctx(), v, u, local_amps(), d_terms, int(terms.size()), 0.0, cim, psi(), cmask, d_partials_,
-                               d_norm);
+                run_pauli_plan(plan, v, u, 0.0, cim, psi(), cmask, d_norm);
                 nrm_change = read_scalar(d_norm);
             } else {
-                k::pauli_apply(ctx(), v, u, local_amps(), d_terms, int(terms.size()), 0.0, cim, nullptr, 0, nullptr, nullptr);
+                run_pauli_plan(plan, v, u, 0.0, cim, nullptr, 0, nullptr);
                 nrm_change = 0.0;
             }
             nrm_change = std::sqrt(allreduce_sum(nrm_change));

@@ -34,6 +34,7 @@ struct CudaErr : std::runtime_error {
 };
 
 class Dist;  // sharded-state communicator (dist.h)
+class ShardPlan;
 
 // RAII: make `device` the calling thread's current CUDA device, restore the previous one on scope exit
 class DeviceGuard {
@@ -55,6 +56,8 @@ public:
 private:
     int prev_ = -1;
 };
+
+struct PauliPlan;  // engine.cpp
 
 struct TermsView {
     size_t n_terms;
@@ -142,10 +145,12 @@ private:
     void run_sharded();
     // schedule everything that can run under the current layout, fuse it and resolve it into `out` (appended); with
     // `eager` all but the last `hold` launches are issued right away (they cannot be part of a remap pipeline's tail)
-    void resolve_phase(int width, std::vector<Launch>& out, bool eager, size_t hold);
+    void resolve_phase(ShardPlan& plan, std::vector<Launch>& out, bool eager, size_t hold);
     void serial_exchange(const std::vector<std::pair<int, int>>& swaps);
     void pipelined_exchange(const std::vector<Launch>& tail, const std::vector<Launch>& head,
                             const std::vector<uint8_t>& slice_bits);
+    void run_pauli_plan(PauliPlan& plan, const double2* in, double2* u, double sre, double sim, double2* acc, uint64_t cmask,
+                        double* d_norm);
     void check_exchange_error();
     bool leaves_from_low_bit(int local_bit, size_t n_swaps) const;
     // CUDA events: a pool, and (start, stop) pairs whose elapsed time is added to a counter once they have completed

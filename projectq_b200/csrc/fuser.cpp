@@ -302,7 +302,7 @@ std::vector<Cluster> Fuser::schedule_impl(int max_qubits, const std::function<bo
             members.push_back(uint32_t(best));
             done[best] = 1;
         }
-        passes.push_back(Cluster{members, int(S.size()), int(G.size())});
+        passes.push_back(Cluster{members, int(S.size()), int(G.size()), S, G});
     }
     return passes;
 }

@@ -36,6 +36,8 @@ struct Cluster {
     std::vector<uint32_t> gates;  // indices into the pending queue, in application order
     int width = 0;
     int n_ctrl = 0;
+    std::vector<uint32_t> targets;  // qubit ids the fused matrix acts on (unordered)
+    std::vector<uint32_t> ctrls;    // controls common to every gate of the pass
 };
 
 class Fuser {

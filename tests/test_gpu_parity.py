@@ -226,6 +226,35 @@ def test_pauli_operators(Backend, make_checker):
         gpu.get_expectation_value([([(0, "X")], 1j)], order)
 
 
+def test_pauli_operators_tiled_paths(Backend, make_checker):
+    """a state wider than one shared-memory tile (16 qubits > 11 tile bits): X/Y terms on every bit (several tile-bit sets),
+    more than 64 terms in one launch group, and terms whose X support is too wide for any tile (global gathers)"""
+    rng = np.random.default_rng(33)
+    n = 16
+    gpu, chk, ids = prepare(Backend, make_checker, n, rng)
+    order = [int(x) for x in rng.permutation(ids)]
+    terms = tfim_terms(n)
+    for _ in range(70):  # random strings of weight 1..5
+        w = int(rng.integers(1, 6))
+        qs = sorted(int(x) for x in rng.permutation(n)[:w])
+        terms.append(([(q, "XYZ"[int(rng.integers(0, 3))]) for q in qs], float(rng.normal())))
+    terms.append(([(q, "X") for q in range(13)], 0.3))                       # wider than a tile
+    terms.append(([(q, "Y" if q % 2 else "X") for q in range(2, 16)], -0.2))  # 14 X/Y factors
+    terms.append(([], 0.4))
+    h1 = sum(abs(c) for _, c in terms)
+    e1 = gpu.get_expectation_value(terms, order)
+    e2 = chk.get_expectation_value(terms, order)
+    assert abs(e1 - e2) < TOL * h1
+    sub = terms[:40] + terms[-3:]
+    gpu.emulate_time_evolution(sub, 0.05, order, [])
+    chk.emulate_time_evolution(sub, 0.05, order, [])
+    assert_same_state(gpu, chk)
+    cterms = [(t, c * (0.3 - 0.2j)) for t, c in terms]
+    gpu.apply_qubit_operator(cterms, order)
+    chk.apply_qubit_operator(cterms, order)
+    assert_same_state(gpu, chk, tol=1e-11 * h1)
+
+
 @pytest.mark.parametrize("ctrl", [[], [8]])
 def test_time_evolution(Backend, make_checker, ctrl):
     rng = np.random.default_rng(5)
