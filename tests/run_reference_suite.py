@@ -39,6 +39,14 @@ if ENGINE == "ours":
     ours.SimulatorBackend = native_mod.Simulator
     projectq.backends.Simulator = ours.Simulator
     projectq.backends._sim.Simulator = ours.Simulator
+    # the unitary backend: the reference's test module does `from ._unitary import UnitarySimulator`
+    import projectq.backends._unitary as ref_unitary  # noqa: E402
+
+    import projectq_b200._unitary as ours_unitary  # noqa: E402
+
+    ours_unitary.SimulatorBackend = native_mod.Simulator
+    ref_unitary.UnitarySimulator = ours_unitary.UnitarySimulator
+    projectq.backends.UnitarySimulator = ours_unitary.UnitarySimulator
 else:
     import projectq.backends._sim._simulator as ref_engine  # noqa: E402
 
@@ -49,6 +57,8 @@ import pytest  # noqa: E402
 
 REF = refenv.REF
 default = [os.path.join(REF, "projectq/backends/_sim/_simulator_test.py"), os.path.join(REF, "projectq/tests/_factoring_test.py")]
+if ENGINE == "ours":
+    default.append(os.path.join(REF, "projectq/backends/_unitary_test.py"))
 args = sys.argv[1:] or default
 print("engine=%s native=%s (%s)" % (ENGINE, "cuda" if NATIVE else "reference", native_mod.Simulator), flush=True)
 sys.exit(pytest.main(["-q", "-p", "no:cacheprovider", "-p", "no:warnings", "--rootdir", "/tmp"] + args))

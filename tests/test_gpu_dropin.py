@@ -49,10 +49,11 @@ def run_suite(engine):
 def test_reference_suite_on_cuda(engine):
     """>= 59 of the reference's 60 Simulator/factoring tests pass with CUDA under the engine.  (With the reference's C++
     simulator exactly one fails here — `numpy.array(list, copy=False)` under NumPy 2, _simulator_test.py:562 — and
-    cheat() returning an ndarray makes even that one pass.)"""
+    cheat() returning an ndarray makes even that one pass.)  Under our engine classes the reference's 8 UnitarySimulator
+    tests (_unitary_test.py) run too, against projectq_b200.UnitarySimulator on the CUDA backend."""
     assert refenv.available(), "reference package not staged (baseline/_ref): run `make -C oracle` in the build container"
     failed, passed, tail = run_suite(engine)
-    assert passed >= 59 and failed <= 1, tail
+    assert passed >= (67 if engine == "ours" else 59) and failed <= 1, tail
 
 
 @pytest.fixture(scope="module")
@@ -90,6 +91,49 @@ def test_baseline_programs_reproduce_the_reference(pq, name):
                     assert np.max(np.abs(np.asarray(val) - np.asarray(gold[key]))) < 1e-11, key
                 else:
                     assert val == gold[key], key  # measured bits: identical for the same rnd_seed
+
+
+def test_unitary_simulator_matches_the_reference_class(pq):
+    """projectq_b200.UnitarySimulator (unitary on the GPU) vs the reference's UnitarySimulator (dense NumPy products) on a
+    random 6-qubit circuit with controls, multi-qubit gates in scrambled target order and a mid-circuit allocation"""
+    from projectq import MainEngine
+    from projectq.backends._unitary import UnitarySimulator as RefUnitary
+    from projectq.meta import Control
+    from projectq.ops import CNOT, H, MatrixGate, Rx, Rz
+
+    from projectq_b200 import UnitarySimulator
+    from tests.helpers import rand_unitary
+
+    def program(backend):
+        rng = np.random.default_rng(12)
+        eng = MainEngine(backend=backend, engine_list=[])
+        q = eng.allocate_qureg(5)
+        for step in range(30):
+            k = int(rng.integers(1, 4))
+            qs = [int(x) for x in rng.permutation(5)[: k + 1]]
+            gate = MatrixGate(rand_unitary(rng, k))
+            if rng.random() < 0.5:
+                with Control(eng, q[qs[k]]):
+                    gate | tuple(q[i] for i in qs[:k])
+            else:
+                gate | tuple(q[i] for i in qs[:k])
+            if step == 12:
+                q = q + eng.allocate_qureg(1)  # U <- 1 (x) U in the middle of the circuit
+                H | q[5]
+                CNOT | (q[5], q[0])
+        Rx(0.3) | q[2]
+        Rz(1.1) | q[5]
+        eng.flush()
+        u = backend.unitary
+        from projectq.ops import All, Measure
+
+        All(Measure) | q
+        eng.flush()
+        return u
+
+    mine, ref = program(UnitarySimulator()), program(RefUnitary())
+    assert mine.shape == ref.shape == (64, 64)
+    assert np.max(np.abs(mine - ref)) < 1e-12
 
 
 def load_shor_example():
