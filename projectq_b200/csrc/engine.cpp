@@ -384,8 +384,9 @@ void Engine::apply_controlled_gate(const double* m, const uint32_t* ids, size_t 
 }
 
 uint64_t Engine::Launch::touched() const {
+    // the same on every rank, also where the pass is switched off: the ranks of an exchange group must agree on the slice
+    // bits of a pipelined remap, which are chosen among the bits the neighbouring passes do not touch
     uint64_t m = 0;
-    if (kind == NONE) return 0;
     for (int l = 0; l < k; ++l) m |= uint64_t(1) << tpos[l];
     for (int l = 0; l < n_ctrl; ++l) m |= uint64_t(1) << cpos[l];
     return m;
@@ -412,7 +413,6 @@ Engine::Launch Engine::resolve_pass(const FusedPass& p) {
     if (p.diagonal) {
         // a diagonal pass needs no remap: targets on rank bits just select a slice of the diagonal for this rank
         ++stats_.diag_passes;
-        if (!active) return out;
         int which[8], kl = 0;
         size_t fixed = 0;
         for (int l = 0; l < kq; ++l) {
@@ -432,11 +432,10 @@ Engine::Launch Engine::resolve_pass(const FusedPass& p) {
             out.m[2 * v + 1] = p.m[idx * D + idx].imag();
         }
         out.k = kl;
-        out.kind = Launch::DIAG;
+        out.kind = active ? Launch::DIAG : Launch::NONE;
         return out;
     }
     ++stats_.dense_passes[kq];
-    if (!active) return out;
     for (int l = 0; l < kq; ++l) {
         const uint32_t lp = map_.at(p.targets[l]);
         if (!is_local(lp)) throw RuntimeErr("internal: dense target on a rank bit was not remapped");
@@ -444,9 +443,11 @@ Engine::Launch Engine::resolve_pass(const FusedPass& p) {
         if (l > 0 && out.tpos[l] <= out.tpos[l - 1]) throw RuntimeErr("internal: pass targets are not in ascending bit order");
     }
     out.k = kq;
-    out.kind = Launch::DENSE;
-    const double* m = reinterpret_cast<const double*>(p.m.data());
-    out.m.assign(m, m + 2 * D * D);
+    out.kind = active ? Launch::DENSE : Launch::NONE;
+    if (active) {
+        const double* m = reinterpret_cast<const double*>(p.m.data());
+        out.m.assign(m, m + 2 * D * D);
+    }
     return out;
 }
 

@@ -137,7 +137,7 @@ private:
         int k = 0, n_ctrl = 0;
         uint8_t tpos[8] = {}, cpos[64] = {};
         std::vector<double> m;  // DENSE: 2^k x 2^k (re,im) row-major; DIAG: 2^k (re,im)
-        uint64_t touched() const;  // mask of the local bits the launch reads as target or control
+        uint64_t touched() const;  // mask of the local bits the pass uses as target or control (rank-independent)
     };
     Launch resolve_pass(const FusedPass& p);
     void launch(const Launch& l, const k::Slice& slice = k::Slice());

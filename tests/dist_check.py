@@ -91,6 +91,29 @@ def main():
     elif expect == "nccl":
         assert st["p2p_remaps"] == 0, st
 
+    # 1b. a longer random circuit with many controls (controls on rank-bit qubits switch whole ranks off, which must not
+    #     change what the ranks of an exchange group agree on), flushed at random points; a second engine so that the first
+    #     one keeps its state for the checks below
+    n2 = 14
+    gpu2, chk2 = make(7), OracleSimulator(7)
+    for q in range(n2):
+        gpu2.allocate_qubit(q)
+        chk2.allocate_qubit(q)
+    wf2 = rand_state(rng, n2)
+    gpu2.set_wavefunction(wf2, list(range(n2)))
+    chk2.set_wavefunction(wf2, list(range(n2)))
+    for g in range(220):
+        k = int(rng.integers(1, 4))
+        nc = int(rng.integers(0, 4))
+        qs = [int(x) for x in rng.permutation(n2)[: k + nc]]
+        m = rand_unitary(rng, k) if rng.random() < 0.85 else np.diag(np.exp(1j * rng.uniform(0, 6.28, 1 << k)))
+        gpu2.apply_controlled_gate(m, qs[:k], qs[k:])
+        chk2.apply_controlled_gate(m, qs[:k], qs[k:])
+        if rng.random() < 0.04:
+            gpu2.run()
+    same(gpu2, chk2, "random circuit with controls")
+    del gpu2, chk2
+
     # 2. queries
     for _ in range(6):
         k = int(rng.integers(1, 5))
