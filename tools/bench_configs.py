@@ -79,12 +79,17 @@ for n in (22, 28):
     ry_layer(sim, n, False)
     e0 = sim.get_expectation_value(tfim_terms(n), list(range(n)))
     tev, texp, e1 = tfim_iteration(sim, n, 0.1, True)
+    sim.reset_stats()
     tev2, texp2, e2 = tfim_iteration(sim, n, 0.1, True)
+    launches = sim.stats()["kernel_launches"]
     amps = float(1 << n)
+    # t = 0.1, ||H||_1 = (n-1) + 0.7 n  ->  s = floor(0.1 * ||H||_1 + 1) sub-steps; the number of Taylor orders per sub-step is
+    # data dependent (until the increment's norm drops below 1e-12): derived from the launch count of one evolution
     emit({"config": "TFIM %d qubits (%d terms): emulate_time_evolution(t=0.1) + get_expectation_value" % (n, 2 * n - 1),
           "gpu_time_evolution_s": min(tev, tev2), "gpu_expectation_s": min(texp, texp2), "E0": e0, "E1": e1, "E2": e2,
-          "energy_drift": abs(e2 - e0), "norm": sim.norm_squared(),
-          "expectation_GBs": (n + 1) * 16.0 * amps / min(texp, texp2) / 1e9})
+          "energy_drift": abs(e2 - e0), "norm": sim.norm_squared(), "kernel_launches_evolution_plus_expectation": launches,
+          "floor_bytes_per_amp_per_taylor_order": 64, "floor_bytes_per_amp_expectation": 16,
+          "expectation_sweeps_equivalent": min(texp, texp2) / (16.0 * amps / 6546.6e9)})
     del sim
     if n == 22 and ref:
         r = ref.Simulator(1)
@@ -120,8 +125,11 @@ def timed(fn, reps=3):
     return best
 
 
+t = timed(lambda: sim.norm_squared())
+emit({"op": "norm_squared 30q (every amplitude read once)", "s": t, "GBs": 16 * amps / t / 1e9})
 t = timed(lambda: sim.get_probability([True, False], [3, 17]))
-emit({"op": "get_probability 30q", "s": t, "GBs": 16 * amps / t / 1e9})
+emit({"op": "get_probability 30q, 2 qubits fixed (a quarter of the amplitudes contribute)", "s": t,
+      "GBs_if_every_amplitude_were_read": 16 * amps / t / 1e9, "GBs_of_contributing_amplitudes": 4 * amps / t / 1e9})
 t = timed(lambda: sim.emulate_math_addConstant(12345, [list(range(4, 16))], [29]))
 emit({"op": "emulate_math_addConstant 12-bit register, 1 control, 30q", "s": t, "GBs_algorithmic(32B/amp)": 32 * amps / t / 1e9})
 t = timed(lambda: sim.emulate_math_multiplyByConstantModN(7, 4087, [list(range(4, 16))], [29]))
