@@ -153,6 +153,18 @@ PQB_API int pqb_get_amplitudes(pqb_sim* sim, const uint64_t* logical_indices, si
  * per gate u32 k, u32 nc, u32 targets[k], u32 ctrls[nc], f64 matrix[2*4^k]; equivalent to n_gates
  * pqb_apply_controlled_gate calls (fuse = 0 additionally calls pqb_run after every gate, like gate_fusion=False) */
 PQB_API int pqb_apply_gate_stream(pqb_sim* sim, const void* packed, size_t n_bytes, size_t n_gates, int fuse);
+/* ---- f3: the state as data, around cheat()/set_wavefunction (simulator.hpp:440-454,529-532) ---------
+ * Checkpoint of the (possibly sharded) state.  Every rank writes / reads its own file "<prefix>.rank<r>of<w>.pqbs": a
+ * header (qubit ids and positions, physical layout, RNG stream position) followed by the shard's amplitudes exactly as they
+ * lie in HBM — nothing is gathered or re-laid-out, so a 36-qubit state (1.1 TB over 8 ranks) is saved and restored shard by
+ * shard.  Loading needs an engine with the same world size and rank; it replaces the engine's qubits, state and RNG. */
+PQB_API int pqb_save_state(pqb_sim* sim, const char* path_prefix);
+PQB_API int pqb_load_state(pqb_sim* sim, const char* path_prefix);
+/* Zero-copy view for consumers that can wrap device memory (CUDA array interface / DLPack producers): the device pointer
+ * of this rank's shard, its length in amplitudes, and for every logical bit position the physical bit it lives on (local
+ * bit < 64, or 64 + rank bit).  The pointer is valid until the next call that allocates, deallocates or remaps. */
+PQB_API int pqb_state_view(pqb_sim* sim, void** out_device_ptr, uint64_t* out_local_amplitudes, uint8_t* out_layout,
+                           size_t layout_capacity, size_t* out_n_qubits);
 /* set |psi> to a seeded pseudo-random normalised state directly on the device (benchmark input), n qubits ids 0..n-1 */
 PQB_API int pqb_init_random_state(pqb_sim* sim, uint32_t n_qubits, uint64_t seed);
 /* sum |psi_i|^2 over the whole state */

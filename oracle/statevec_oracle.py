@@ -10,7 +10,8 @@ Parity pinning: ``tests/test_oracle_pinned.py`` checks this restatement against
     random circuits, and
   * the golden vectors generated from that reference (`tests/golden/*.json`, generator
     `tests/golden/make_golden.py`) and the known answers held by the reference's own tests
-    (`_simulator_test.py:744` etc., restated in `tests/golden/reference_kats.json`).
+    (`_simulator_test.py:744` etc., restated in `tests/test_gpu_parity.py::test_reference_math_kats` and
+    `tests/test_oracle_pinned.py`).
 
 Each method cites the reference lines it follows (paths relative to /root/reference/projectq/backends/_sim).
 Gate fusion is *not* restated: any fusion policy is amplitude-equivalent (simulator.hpp:204-222 only

@@ -123,6 +123,17 @@ class Simulator(BasicEngine):
         """(id -> bit position dict, state vector as a NumPy complex128 array) (reference: _simulator.py:301-322)."""
         return self._simulator.cheat()
 
+    # ---- additions: the state as data (SURVEY §8f rank 3) -------------------------------------------------------
+    def save_state(self, path_prefix):
+        """Write the state, the qubit map and the RNG position to ``<path_prefix>.rank<r>of<w>.pqbs`` (one file per GPU of a
+        sharded run; nothing is gathered).  Call ``eng.flush()`` first."""
+        self._simulator.save_state(str(path_prefix))
+
+    def load_state(self, path_prefix):
+        """Replace the simulator's qubits, state and RNG position by a checkpoint written with ``save_state``.  The program
+        must hold qubits with the same ids (allocate the same registers in the same order, ``eng.flush()``, then load)."""
+        self._simulator.load_state(str(path_prefix))
+
     # ---- command handling --------------------------------------------------------------------------------------
     def _handle(self, cmd):
         """Dispatch one command to the native backend (reference: _simulator.py:324-420)."""

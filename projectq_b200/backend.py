@@ -22,3 +22,16 @@ selftest_exchange = _pqb_shim.selftest_exchange
 def load_c_abi():
     """ctypes handle on libpqb200.so (used by the symbol-export test and by bindings that skip pybind11)."""
     return ctypes.CDLL(LIB_PATH)
+
+
+class DeviceStateView:
+    """Zero-copy handle on a backend's state in HBM: exposes ``__cuda_array_interface__`` (complex128, one entry per local
+    amplitude) so that ``torch.as_tensor(view, device="cuda")``, ``cupy.asarray(view)`` or numba wrap the memory without a
+    copy.  ``layout[p]`` is the physical bit of logical bit position p (local bit < 64, else 64 + rank bit).  Keeps the
+    backend alive; the memory is only valid until the next call that allocates, deallocates or remaps qubits."""
+
+    def __init__(self, backend):
+        info = backend.state_view()
+        self._backend = backend
+        self.__cuda_array_interface__ = info["cuda_array_interface"]
+        self.layout = list(info["layout"])

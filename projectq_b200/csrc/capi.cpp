@@ -206,6 +206,15 @@ int pqb_get_amplitudes(pqb_sim* s, const uint64_t* idx, size_t n, double* out) {
 int pqb_apply_gate_stream(pqb_sim* s, const void* packed, size_t n_bytes, size_t n_gates, int fuse) {
     return guarded(s, [&](Engine& e) { e.apply_gate_stream(packed, n_bytes, n_gates, fuse != 0); });
 }
+int pqb_save_state(pqb_sim* s, const char* prefix) {
+    return guarded(s, [&](Engine& e) { e.save_state(prefix ? prefix : ""); });
+}
+int pqb_load_state(pqb_sim* s, const char* prefix) {
+    return guarded(s, [&](Engine& e) { e.load_state(prefix ? prefix : ""); });
+}
+int pqb_state_view(pqb_sim* s, void** ptr, uint64_t* n_amps, uint8_t* layout, size_t cap, size_t* n_qubits) {
+    return guarded(s, [&](Engine& e) { e.state_view(ptr, n_amps, layout, cap, n_qubits); });
+}
 int pqb_init_random_state(pqb_sim* s, uint32_t n, uint64_t seed) {
     return guarded(s, [&](Engine& e) { e.init_random_state(n, seed); });
 }

@@ -88,6 +88,7 @@ public:
     bool has_free_rank_bit() const { return free_mask_ != 0; }
     int take_free_rank_bit();
     void reset_rank_bits(int n_used);  // rank bits [0, n_used) carry qubits, the rest are free
+    void set_free_rank_bits_mask(uint64_t m) { free_mask_ = m & ((uint64_t(1) << g_) - 1); }  // restoring a checkpoint
     // the qubit on rank bit r was found classical with `value`: move the surviving shards onto bit r = 0, free the bit
     void release_rank_bit(int r, bool value, double2* shard, uint64_t n_amps);
     // exchange rank bit r with local bit b (n_local_bits = log2 n_amps); staging: >= staging_amps device amplitudes

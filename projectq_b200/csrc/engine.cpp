@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cmath>
 #include <set>
+#include <sstream>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -1260,7 +1262,10 @@ static void to_physical(std::vector<k::PauliTerm>& terms, const std::vector<uint
 // support is too large for any tile are returned in `wide` and go through per-term global gathers.
 struct PauliPlan {
     std::vector<k::PauliTileArgs> launches;  // in execution order; first/final/scale are filled in by the caller
+    std::vector<long> table_at;              // per launch: offset of its diagonal table in `tables`, or -1
+    std::vector<double2> tables;             // 2^T entries per table
     std::vector<k::PauliTerm> wide;
+    const k::PauliTerm* d_wide = nullptr;
 };
 
 static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
@@ -1285,17 +1290,55 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
         base.T_lo = 0;
         while (base.T_lo < T && base.tile_pos[base.T_lo] == base.T_lo) ++base.T_lo;
         base.n_tiles = uint64_t(1) << (L - T);
-        size_t at = 0;
+        // diagonal terms with z inside the tile -> one table for the whole pass
+        std::vector<double2> table;
+        std::vector<int> generic, outside;
+        for (int i : members) {
+            const k::PauliTerm& tm = terms[i];
+            if (tm.xmask != 0) {
+                generic.push_back(i);
+            } else if ((tm.zmask & ~S) == 0) {
+                if (table.empty()) table.assign(size_t(1) << T, make_double2(0.0, 0.0));
+                const uint32_t zl = uint32_t(extract_bits(tm.zmask, base.tile_pos, T));
+                for (uint32_t t = 0; t < (1u << T); ++t) {
+                    const bool neg = __builtin_popcount(t & zl) & 1;
+                    table[t].x += neg ? -tm.cre : tm.cre;
+                    table[t].y += neg ? -tm.cim : tm.cim;
+                }
+            } else if ((tm.zmask & S) == 0) {
+                outside.push_back(i);
+            } else {
+                generic.push_back(i);
+            }
+        }
+        size_t at_g = 0, at_o = 0;
+        bool first_chunk = true;
         do {
             k::PauliTileArgs a = base;
-            for (; at < members.size() && a.n_terms < k::kTileTerms; ++at) {
-                const k::PauliTerm& tm = terms[members[at]];
-                a.t[a.n_terms] = tm;
+            for (; at_g < generic.size() && a.n_terms < k::kTileTerms; ++at_g) {
+                const k::PauliTerm& tm = terms[generic[at_g]];
+                a.coef[a.n_terms] = make_double2(tm.cre, tm.cim);
                 a.xl[a.n_terms] = uint32_t(extract_bits(tm.xmask, base.tile_pos, T));
+                a.zl[a.n_terms] = uint32_t(extract_bits(tm.zmask, base.tile_pos, T));
+                a.z_out[a.n_terms] = tm.zmask & ~S;
+                if (a.zl[a.n_terms] != 0) a.any_zl = 1;
                 ++a.n_terms;
             }
+            for (; at_o < outside.size() && a.n_outside < k::kTileTerms; ++at_o) {
+                const k::PauliTerm& tm = terms[outside[at_o]];
+                a.coef_outside[a.n_outside] = make_double2(tm.cre, tm.cim);
+                a.z_outside[a.n_outside] = tm.zmask;
+                ++a.n_outside;
+            }
+            long at = -1;
+            if (first_chunk && !table.empty()) {
+                at = long(plan.tables.size());
+                plan.tables.insert(plan.tables.end(), table.begin(), table.end());
+            }
             plan.launches.push_back(a);
-        } while (at < members.size());
+            plan.table_at.push_back(at);
+            first_chunk = false;
+        } while (at_g < generic.size() || at_o < outside.size());
     };
     while (!todo.empty()) {
         uint64_t S = low2 | terms[todo[0]].xmask;  // the oldest uncovered term always fits: progress is guaranteed
@@ -1321,14 +1364,25 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
     return plan;
 }
 
+// tables and wide terms go to the device in one upload; the launches get their device pointers
+void Engine::upload_pauli_plan(PauliPlan& plan) {
+    const size_t table_bytes = plan.tables.size() * sizeof(double2), wide_bytes = plan.wide.size() * sizeof(k::PauliTerm);
+    if (table_bytes + wide_bytes == 0) return;
+    std::vector<char> blob(table_bytes + wide_bytes);
+    if (table_bytes) std::memcpy(blob.data(), plan.tables.data(), table_bytes);
+    if (wide_bytes) std::memcpy(blob.data() + table_bytes, plan.wide.data(), wide_bytes);
+    const char* d = static_cast<const char*>(small_upload(blob.data(), blob.size()));
+    for (size_t i = 0; i < plan.launches.size(); ++i)
+        plan.launches[i].w_in = plan.table_at[i] >= 0 ? reinterpret_cast<const double2*>(d) + plan.table_at[i] : nullptr;
+    plan.d_wide = wide_bytes ? reinterpret_cast<const k::PauliTerm*>(d + table_bytes) : nullptr;
+}
+
 // u <- scale * sum_t c_t P_t in   (and optionally acc += u on the control subspace with |u|^2 summed into d_norm)
 void Engine::run_pauli_plan(PauliPlan& plan, const double2* in, double2* u, double sre, double sim, double2* acc, uint64_t cmask,
                             double* d_norm) {
     bool first = true;
     if (!plan.wide.empty()) {
-        const k::PauliTerm* d_terms =
-            static_cast<const k::PauliTerm*>(small_upload(plan.wide.data(), plan.wide.size() * sizeof(k::PauliTerm)));
-        k::pauli_gather_accumulate(ctx(), in, u, local_amps(), d_terms, int(plan.wide.size()), true);
+        k::pauli_gather_accumulate(ctx(), in, u, local_amps(), plan.d_wide, int(plan.wide.size()), true);
         first = false;
     }
     for (size_t i = 0; i < plan.launches.size(); ++i) {
@@ -1381,8 +1435,9 @@ double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, si
         if (!active) continue;
         // tile-able terms: one read of the state per tile-bit set; the rest: one pair sweep per distinct xmask
         PauliPlan plan = plan_pauli_tiles(batch, L_);
+        upload_pauli_plan(plan);
         for (auto& a : plan.launches) {
-            if (a.n_terms == 0) continue;
+            if (a.n_terms == 0 && a.n_outside == 0 && a.w_in == nullptr) continue;
             a.expectation = 1;
             const int grid = k::pauli_tile_pass(ctx(), psi(), nullptr, nullptr, a, d_partials_);
             k::reduce_partials(ctx(), d_partials_, grid, d_acc, true);
@@ -1422,6 +1477,7 @@ void Engine::apply_qubit_operator(const TermsView& t, const uint32_t* ids, size_
     const size_t bytes = local_amps() * sizeof(double2);
     ensure_scratch(*scratch1_, bytes);
     PauliPlan plan = plan_pauli_tiles(terms, L_);
+    upload_pauli_plan(plan);
     run_pauli_plan(plan, psi(), scratch1_->amps(), 1.0, 0.0, nullptr, 0, nullptr);
     std::swap(state_, scratch1_);
 }
@@ -1454,6 +1510,7 @@ void Engine::emulate_time_evolution(const TermsView& t, double time, const uint3
     ensure_scratch(*scratch1_, bytes);
     ensure_scratch(*scratch2_, bytes);
     PauliPlan plan = plan_pauli_tiles(terms, L_);
+    upload_pauli_plan(plan);
     double* d_norm = d_scalars_;
     for (unsigned i = 0; i < s; ++i) {
         double2* v = scratch1_->amps();
@@ -1539,6 +1596,145 @@ void Engine::init_random_state(uint32_t n_qubits, uint64_t seed) {
         PQB_CHECK(cudaMemsetAsync(psi(), 0, local_amps() * sizeof(double2), stream_));
     const double nrm = norm_squared();
     k::scale_all(ctx(), psi(), local_amps(), 1.0 / std::sqrt(nrm));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// checkpoint / view (f3)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kIoChunk = size_t(64) << 20;  // pinned staging buffer between HBM and the file
+
+std::string shard_file(const std::string& prefix, int rank, int world) {
+    return prefix + ".rank" + std::to_string(rank) + "of" + std::to_string(world) + ".pqbs";
+}
+
+struct FileCloser {
+    FILE* f;
+    ~FileCloser() {
+        if (f) fclose(f);
+    }
+};
+}  // namespace
+
+void Engine::save_state(const std::string& prefix) {
+    run();
+    const std::string path = shard_file(prefix, rank_, world_);
+    FileCloser fc{fopen(path.c_str(), "wb")};
+    if (!fc.f) throw RuntimeErr("save_state(): cannot open " + path);
+    auto put = [&](const void* p, size_t n) {
+        if (n && fwrite(p, 1, n, fc.f) != n) throw RuntimeErr("save_state(): write failed on " + path);
+    };
+    std::ostringstream rng_text;
+    rng_text << rng_;
+    const std::string rng = rng_text.str();
+    const uint32_t head[8] = {1 /*version*/, uint32_t(n_), uint32_t(L_), uint32_t(rank_), uint32_t(world_),
+                              uint32_t(rng.size()), 0, 0};
+    const uint64_t free_mask = dist_ ? dist_->free_rank_bits_mask() : 0;
+    put("PQBS", 4);
+    put(head, sizeof(head));
+    put(&free_mask, 8);
+    for (auto& kv : map_) {
+        const uint32_t e[2] = {kv.first, kv.second};
+        put(e, 8);
+    }
+    put(loc_.data(), size_t(n_));
+    put(rng.data(), rng.size());
+    // the shard, as it lies in HBM
+    void* pinned = nullptr;
+    PQB_CHECK(cudaMallocHost(&pinned, kIoChunk));
+    try {
+        const size_t total = local_amps() * sizeof(double2);
+        for (size_t off = 0; off < total; off += kIoChunk) {
+            const size_t cnt = std::min(kIoChunk, total - off);
+            PQB_CHECK(cudaMemcpyAsync(pinned, reinterpret_cast<const char*>(psi()) + off, cnt, cudaMemcpyDeviceToHost, stream_));
+            PQB_CHECK(cudaStreamSynchronize(stream_));
+            put(pinned, cnt);
+        }
+    } catch (...) {
+        cudaFreeHost(pinned);
+        throw;
+    }
+    cudaFreeHost(pinned);
+    if (fflush(fc.f) != 0) throw RuntimeErr("save_state(): write failed on " + path);
+}
+
+void Engine::load_state(const std::string& prefix) {
+    run();
+    const std::string path = shard_file(prefix, rank_, world_);
+    FileCloser fc{fopen(path.c_str(), "rb")};
+    if (!fc.f) throw RuntimeErr("load_state(): cannot open " + path);
+    auto get = [&](void* p, size_t n) {
+        if (n && fread(p, 1, n, fc.f) != n) throw RuntimeErr("load_state(): " + path + " is truncated");
+    };
+    char magic[4];
+    uint32_t head[8];
+    uint64_t free_mask = 0;
+    get(magic, 4);
+    get(head, sizeof(head));
+    get(&free_mask, 8);
+    if (std::memcmp(magic, "PQBS", 4) != 0 || head[0] != 1) throw ValueErr("load_state(): " + path + " is not a state checkpoint");
+    const uint32_t n = head[1], L = head[2];
+    if (int(head[3]) != rank_ || int(head[4]) != world_)
+        throw ValueErr("load_state(): the checkpoint was written by rank " + std::to_string(head[3]) + " of " +
+                       std::to_string(head[4]) + ", this engine is rank " + std::to_string(rank_) + " of " +
+                       std::to_string(world_));
+    if (n > 62 || L > n || head[5] > (1u << 20)) throw ValueErr("load_state(): corrupt header in " + path);
+    std::map<uint32_t, uint32_t> map;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t e[2];
+        get(e, 8);
+        if (e[1] >= n) throw ValueErr("load_state(): corrupt qubit map in " + path);
+        map[e[0]] = e[1];
+    }
+    std::vector<uint8_t> loc(n);
+    get(loc.data(), n);
+    std::string rng(head[5], '\0');
+    get(&rng[0], rng.size());
+    if (map.size() != n) throw ValueErr("load_state(): corrupt qubit map in " + path);
+    const size_t total = (sizeof(double2) << L);
+    try {
+        state_->ensure(total, stream_);
+    } catch (const std::bad_alloc&) {
+        scratch1_->release();
+        scratch2_->release();
+        try {
+            state_->ensure(total, stream_);
+        } catch (const std::bad_alloc&) {
+            throw CudaErr("load_state(): out of device memory");
+        }
+    }
+    void* pinned = nullptr;
+    PQB_CHECK(cudaMallocHost(&pinned, kIoChunk));
+    try {
+        for (size_t off = 0; off < total; off += kIoChunk) {
+            const size_t cnt = std::min(kIoChunk, total - off);
+            get(pinned, cnt);
+            PQB_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(state_->ptr()) + off, pinned, cnt, cudaMemcpyHostToDevice, stream_));
+            PQB_CHECK(cudaStreamSynchronize(stream_));
+        }
+    } catch (...) {
+        cudaFreeHost(pinned);
+        throw;
+    }
+    cudaFreeHost(pinned);
+    // commit the bookkeeping only after the data is in place
+    map_.swap(map);
+    loc_.swap(loc);
+    n_ = int(n);
+    L_ = int(L);
+    if (dist_) dist_->set_free_rank_bits_mask(free_mask);
+    std::istringstream rng_text(rng);
+    rng_text >> rng_;
+}
+
+void Engine::state_view(void** ptr, uint64_t* n_amps, uint8_t* layout, size_t cap, size_t* n_qubits) {
+    run();
+    PQB_CHECK(cudaStreamSynchronize(stream_));
+    if (ptr) *ptr = state_->ptr();
+    if (n_amps) *n_amps = local_amps();
+    if (n_qubits) *n_qubits = size_t(n_);
+    if (layout)
+        for (int p = 0; p < n_ && size_t(p) < cap; ++p) layout[p] = loc_[p];
 }
 
 void Engine::synchronize() {

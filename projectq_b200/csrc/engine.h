@@ -99,6 +99,9 @@ public:
     void get_amplitudes(const uint64_t* logical_idx, size_t n, double* out);
     void apply_gate_stream(const void* packed, size_t n_bytes, size_t n_gates, bool fuse);
     void init_random_state(uint32_t n_qubits, uint64_t seed);
+    void save_state(const std::string& prefix);
+    void load_state(const std::string& prefix);
+    void state_view(void** ptr, uint64_t* n_amps, uint8_t* layout, size_t cap, size_t* n_qubits);
     double norm_squared();
     void synchronize();
     void timer_start();
@@ -149,6 +152,7 @@ private:
     void serial_exchange(const std::vector<std::pair<int, int>>& swaps);
     void pipelined_exchange(const std::vector<Launch>& tail, const std::vector<Launch>& head,
                             const std::vector<uint8_t>& slice_bits);
+    void upload_pauli_plan(PauliPlan& plan);
     void run_pauli_plan(PauliPlan& plan, const double2* in, double2* u, double sre, double sim, double2* acc, uint64_t cmask,
                         double* d_norm);
     void check_exchange_error();

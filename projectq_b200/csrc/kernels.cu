@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -243,6 +244,88 @@ __global__ void __launch_bounds__(THREADS, MINB) apply_dense_lowbits_kernel(doub
     }
 }
 
+// MODE 3 (separate kernel): k = 4 with targets exactly {0,1,2,3} — a group is one contiguous 256-byte run and neighbouring
+// threads are 256 bytes apart, the worst case for per-lane accesses (32 lines per request: measured 6.85 ms against 4.95 ms
+// for a mid placement at 30 qubits, with 7 % write amplification).  Here no thread touches global memory at all: every
+// thread asks the TMA unit for its own run (cp.async.bulk global -> shared, completion counted on one mbarrier per CTA),
+// reads it back with 16 conflict-free 128-bit shared loads (row pitch 272 bytes = 17 slots of 16 bytes, so the 8 threads
+// of a quarter-warp hit 8 different bank groups), writes the 16 results into the same row and hands the row back to the
+// TMA unit (cp.async.bulk shared -> global).  The load/store pipe carries 32 shared-memory operations per thread and no
+// LDG/STG; three CTAs (3 x 68 KB of shared memory) are resident per SM so that one CTA's transfers overlap another's math.
+constexpr int kTmaRowBytes = 272;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) apply_dense_k4_low_tma_kernel(double2* __restrict__ psi,
+                                                                         const __grid_constant__ DenseArgs<4> p) {
+    constexpr int K = 4, D = 16;
+    extern __shared__ __align__(128) unsigned char rows[];
+    __shared__ __align__(8) unsigned long long bar;
+    const uint64_t g = uint64_t(blockIdx.x) * THREADS + threadIdx.x;
+    const bool valid = g < p.n_items;
+    const uint64_t n_valid = p.n_items - uint64_t(blockIdx.x) * THREADS < uint64_t(THREADS)
+                                 ? p.n_items - uint64_t(blockIdx.x) * THREADS
+                                 : uint64_t(THREADS);
+    double2* run = psi + (insert_zero_bits(g, p.ins_pos, p.n_ins) | p.ctrl_mask);
+    unsigned char* row = rows + threadIdx.x * kTmaRowBytes;
+    const uint32_t row_s = smem_addr(row), bar_s = smem_addr(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(uint32_t(n_valid * 256)) : "memory");
+    }
+    __syncthreads();
+    if (valid)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(row_s),
+                     "l"(run), "r"(256), "r"(bar_s)
+                     : "memory");
+    uint32_t done = 0;
+    while (!done)
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(bar_s), "r"(0)
+            : "memory");
+    if (!valid) return;
+    double2 v[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) v[j] = *reinterpret_cast<const double2*>(row + j * 16);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double re, im;
+        matvec_row<K>(p, v, i, re, im);
+        *reinterpret_cast<double2*>(row + i * 16) = make_double2(re, im);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(run), "r"(row_s), "r"(256) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the row must stay intact until the TMA unit has read it
+}
+
+static bool dense_tma_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("PQB_DENSE_TMA");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+static void launch_dense_k4_low_tma(const Ctx& c, double2* psi, const DenseArgs<4>& args) {
+    constexpr int THREADS = 256, MINB = 3;
+    constexpr size_t smem = size_t(THREADS) * kTmaRowBytes;
+    static bool configured = false;
+    if (!configured) {
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(apply_dense_k4_low_tma_kernel<THREADS, MINB>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = true;
+    }
+    const uint64_t blocks = (args.n_items + THREADS - 1) / THREADS;
+    if (blocks > 0x7fffffffULL) throw std::invalid_argument("apply_dense: grid too large");
+    apply_dense_k4_low_tma_kernel<THREADS, MINB><<<unsigned(blocks), THREADS, smem, c.stream>>>(psi, args);
+    launched(c);
+}
+
 template <int K, int C, int THREADS, int MINB>
 static void launch_dense_lowbits(const Ctx& c, double2* psi, const DenseArgs<K>& args) {
     constexpr int ROW = (1 << C) + 1;
@@ -333,6 +416,9 @@ static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* 
             const int cb = lowbits_run<K>(args, n_bits);
             if (cb == 2) return launch_dense_lowbits<K, 2, 256, 2>(c, psi, args);
             if (cb == 3) return launch_dense_lowbits<K, 3, 256, 2>(c, psi, args);
+        }
+        if constexpr (K == 4) {
+            if (dense_tma_enabled() && tpos[1] == 1 && tpos[2] == 2 && tpos[3] == 3) return launch_dense_k4_low_tma(c, psi, args);
         }
         launch_dense_mode<K, 1, 1, (K >= 5 ? 128 : 256), (K == 3 ? 2 : (K <= 2 ? 4 : 3))>(c, psi, args);
     } else {
@@ -1097,37 +1183,82 @@ __global__ void __launch_bounds__(THREADS) pauli_tile_kernel(const double2* __re
                                                              const __grid_constant__ PauliTileArgs a,
                                                              double* __restrict__ partials) {
     extern __shared__ double2 tile[];
+    __shared__ double2 coef_s[kTileTerms];  // coefficients with this tile's outside-z sign applied
+    __shared__ double2 w_out_s;             // sum of the outside-only diagonal terms for this tile
     const int tile_amps = 1 << a.T;
-    const uint32_t lo_mask = (1u << a.T_lo) - 1;
+    constexpr int LOG_THREADS = THREADS == 256 ? 8 : 7;
+    // index bits of this thread's elements that do not depend on the tile: element e of the thread has tile coordinate
+    // t = e * THREADS + tid, whose low bits are tid
+    const int n_e = tile_amps > THREADS ? tile_amps / THREADS : 1;
+    auto coord_to_index = [&](uint32_t t) {
+        const uint32_t lo_mask = (1u << a.T_lo) - 1;
+        return uint64_t(t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
+    };
+    const uint64_t g_tid = coord_to_index(threadIdx.x & (tile_amps - 1));
     double red = 0.0;
     for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x) {
         const uint64_t base = insert_zero_bits(tid_tile, a.tile_pos, a.T);
-        __syncthreads();  // the previous tile is no longer needed
-        for (int t = threadIdx.x; t < tile_amps; t += THREADS) {
-            const uint64_t g = base | (t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
-            tile[t] = in[g];
+        __syncthreads();  // the previous tile (and its coefficients) is no longer needed
+        if (int(threadIdx.x) < a.n_terms) {
+            double2 c = a.coef[threadIdx.x];
+            if (__popcll(base & a.z_out[threadIdx.x]) & 1) c = make_double2(-c.x, -c.y);
+            coef_s[threadIdx.x] = c;
+        }
+        if (threadIdx.x == THREADS - 1) {
+            double wr = 0.0, wi = 0.0;
+            for (int k = 0; k < a.n_outside; ++k) {
+                const bool neg = __popcll(base & a.z_outside[k]) & 1;
+                wr += neg ? -a.coef_outside[k].x : a.coef_outside[k].x;
+                wi += neg ? -a.coef_outside[k].y : a.coef_outside[k].y;
+            }
+            w_out_s = make_double2(wr, wi);
+        }
+        for (int e = 0; e < n_e; ++e) {
+            const uint32_t t = uint32_t(e) * THREADS + threadIdx.x;
+            if (t < uint32_t(tile_amps)) tile[t] = in[base | g_tid | coord_to_index(uint32_t(e) << LOG_THREADS)];
         }
         __syncthreads();
-        for (int t = threadIdx.x; t < tile_amps; t += THREADS) {
-            const uint64_t g = base | (t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
-            double re = 0.0, im = 0.0;
-            for (int k = 0; k < a.n_terms; ++k) {
-                const double2 v = tile[t ^ a.xl[k]];
-                double cr = a.t[k].cre, ci = a.t[k].cim;
-                if (__popcll((g ^ a.t[k].xmask) & a.t[k].zmask) & 1) {
-                    cr = -cr;
-                    ci = -ci;
+        const double2 w_out = w_out_s;
+        for (int e = 0; e < n_e; ++e) {
+            const uint32_t t = uint32_t(e) * THREADS + threadIdx.x;
+            if (t >= uint32_t(tile_amps)) break;
+            const double2 self = tile[t];
+            // diagonal part: (table of in-tile terms + per-tile scalar) * psi_j
+            double wr = w_out.x, wi = w_out.y;
+            if (a.w_in != nullptr) {
+                const double2 w = __ldg(a.w_in + t);
+                wr += w.x;
+                wi += w.y;
+            }
+            double re = wr * self.x - wi * self.y, im = wr * self.y + wi * self.x;
+            if (a.any_zl) {
+#pragma unroll 2
+                for (int k = 0; k < a.n_terms; ++k) {
+                    const uint32_t s = t ^ a.xl[k];
+                    const double2 v = tile[s];
+                    double2 c = coef_s[k];
+                    if (__popc(s & a.zl[k]) & 1) c = make_double2(-c.x, -c.y);
+                    re = fma(c.x, v.x, re);
+                    re = fma(-c.y, v.y, re);
+                    im = fma(c.x, v.y, im);
+                    im = fma(c.y, v.x, im);
                 }
-                re = fma(cr, v.x, re);
-                re = fma(-ci, v.y, re);
-                im = fma(cr, v.y, im);
-                im = fma(ci, v.x, im);
+            } else {  // pure X strings (every term of a transverse field): no per-amplitude signs
+#pragma unroll 4
+                for (int k = 0; k < a.n_terms; ++k) {
+                    const double2 v = tile[t ^ a.xl[k]];
+                    const double2 c = coef_s[k];
+                    re = fma(c.x, v.x, re);
+                    re = fma(-c.y, v.y, re);
+                    im = fma(c.x, v.y, im);
+                    im = fma(c.y, v.x, im);
+                }
             }
             if (a.expectation) {
-                const double2 p = tile[t];
-                red += p.x * re + p.y * im;  // Re(conj(psi_j) s_j)
+                red += self.x * re + self.y * im;  // Re(conj(psi_j) s_j)
                 continue;
             }
+            const uint64_t g = base | g_tid | coord_to_index(uint32_t(e) << LOG_THREADS);
             if (!a.first) {
                 const double2 prev = u[g];
                 re += prev.x;
@@ -1153,7 +1284,8 @@ __global__ void __launch_bounds__(THREADS) pauli_tile_kernel(const double2* __re
 }
 
 int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs& a, double* d_partials) {
-    if (a.T > 12 || a.T < 0 || a.n_terms > kTileTerms) throw std::invalid_argument("pauli_tile_pass: bad arguments");
+    if (a.T > 12 || a.T < 0 || a.n_terms > kTileTerms || a.n_outside > kTileTerms)
+        throw std::invalid_argument("pauli_tile_pass: bad arguments");
     constexpr int THREADS = 256;
     const size_t smem = sizeof(double2) << a.T;
     static bool configured = false;

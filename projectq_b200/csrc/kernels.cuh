@@ -145,10 +145,22 @@ void pauli_apply(const Ctx& c, const double2* in, double2* out, uint64_t n_amps,
 // gather stream per distinct xmask.
 constexpr int kTileBits = 11;       // 2^11 amplitudes = 32 KB of shared memory per CTA
 constexpr int kTileTerms = 64;      // terms per launch
+// Everything the kernel needs is expressed in tile coordinates (bit i of a tile coordinate = index bit tile_pos[i]), so the
+// per-amplitude work is 32-bit: a term's sign (-1)^{popcount(s & zmask)} on the source index s = j ^ xmask factors into a
+// per-tile factor from the z bits outside the tile (s and j agree there; applied to the coefficient once per tile, in
+// shared memory) and a per-amplitude factor from the z bits inside the tile, taken on the source's tile coordinate.  Diagonal terms (xmask = 0) are split three ways: z entirely inside the tile -> one host-built table
+// w_in[tile coordinate] shared by all tiles; z entirely outside -> one scalar per tile; the rest are treated like any term.
 struct PauliTileArgs {
-    PauliTerm t[kTileTerms];
-    uint32_t xl[kTileTerms];        // xmask of each term in tile coordinates
+    double2 coef[kTileTerms];       // c_t * i^{nY}
+    uint64_t z_out[kTileTerms];     // z bits outside the tile (index positions)
+    uint32_t xl[kTileTerms];        // xmask in tile coordinates (0 for a diagonal term)
+    uint32_t zl[kTileTerms];        // z bits inside the tile, in tile coordinates
     int n_terms;
+    int any_zl;                     // 0: no term of this launch has z bits inside the tile (no per-amplitude signs)
+    double2 coef_outside[kTileTerms];  // diagonal terms with z entirely outside the tile
+    uint64_t z_outside[kTileTerms];
+    int n_outside;
+    const double2* w_in;            // sum of the diagonal terms with z inside the tile, per tile coordinate (or nullptr)
     int T, T_lo;                    // tile bits; the lowest T_lo of them are the index bits 0..T_lo-1
     uint8_t tile_pos[16];           // ascending
     uint64_t n_tiles;

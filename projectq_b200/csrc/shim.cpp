@@ -295,6 +295,43 @@ public:
         }
         check(st);
     }
+    void save_state(const std::string& prefix) {
+        int st;
+        {
+            py::gil_scoped_release nogil;
+            st = pqb_save_state(sim_, prefix.c_str());
+        }
+        check(st);
+    }
+    void load_state(const std::string& prefix) {
+        int st;
+        {
+            py::gil_scoped_release nogil;
+            st = pqb_load_state(sim_, prefix.c_str());
+        }
+        check(st);
+    }
+    // zero-copy: a dict in the CUDA array interface (v3) format plus the qubit layout; wrap it with any consumer of
+    // __cuda_array_interface__ (torch.as_tensor, cupy.asarray, numba) through projectq_b200.backend.DeviceStateView
+    py::dict state_view() {
+        void* ptr = nullptr;
+        uint64_t n_amps = 0;
+        uint8_t layout[64] = {0};
+        size_t n = 0;
+        check(pqb_state_view(sim_, &ptr, &n_amps, layout, 64, &n));
+        py::dict cai;
+        cai["shape"] = py::make_tuple(n_amps);
+        cai["typestr"] = "<c16";
+        cai["data"] = py::make_tuple(reinterpret_cast<uintptr_t>(ptr), false);
+        cai["version"] = 3;
+        cai["strides"] = py::none();
+        py::list lay;
+        for (size_t p = 0; p < n; ++p) lay.append(int(layout[p]));
+        py::dict out;
+        out["cuda_array_interface"] = cai;
+        out["layout"] = lay;
+        return out;
+    }
     void init_random_state(uint32_t n, uint64_t seed) { check(pqb_init_random_state(sim_, n, seed)); }
     double norm_squared() {
         double v = 0.0;
@@ -434,6 +471,9 @@ PYBIND11_MODULE(_pqb_shim, m) {
         .def("apply_gate_stream", &Simulator::apply_gate_stream, py::arg("packed"), py::arg("n_gates"),
              py::arg("fuse") = true)
         .def("apply_gate_list", &Simulator::apply_gate_list, py::arg("gates"), py::arg("fuse") = true)
+        .def("save_state", &Simulator::save_state)
+        .def("load_state", &Simulator::load_state)
+        .def("state_view", &Simulator::state_view)
         .def("init_random_state", &Simulator::init_random_state)
         .def("norm_squared", &Simulator::norm_squared)
         .def("synchronize", &Simulator::synchronize)

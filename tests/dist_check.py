@@ -197,6 +197,25 @@ def main():
             gpu.run()
     err = same(gpu, chk, "brickwork 20q")
     st = gpu.stats()
+
+    # 7. checkpoint of the sharded state: every rank writes and reads its own shard file, nothing is gathered
+    prefix = "/tmp/pqb_ckpt_%s" % os.environ.get("MASTER_PORT", "0")
+    gpu.save_state(prefix)
+    dist.barrier()
+    other = make(77)
+    other.load_state(prefix)
+    same(other, chk, "checkpoint restore")
+    m = rand_unitary(rng, 3)
+    other.apply_controlled_gate(m, [0, 19, 7], [3])
+    chk.apply_controlled_gate(m, [0, 19, 7], [3])
+    same(other, chk, "gates after restore")
+    assert list(other.measure_qubits([19, 2])) == list(chk.measure_qubits([19, 2]))
+    del other
+    dist.barrier()
+    try:
+        os.remove("%s.rank%dof%d.pqbs" % (prefix, rank, world))
+    except OSError:
+        pass
     if rank == 0:
         print("dist_check OK: world=%d, brickwork max|dpsi|=%.2e, stats=%s" % (world, err, st), flush=True)
     dist.barrier()

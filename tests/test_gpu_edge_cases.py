@@ -276,3 +276,86 @@ def test_exchange_kernel_permutation_single_device():
                                               (8, 14, [(2, 4), (0, 6), (1, 13)], 1 << 12), (8, 13, [(1, 12)], 0),
                                               (4, 4, [(0, 3), (1, 2)], 0b01), (2, 1, [(0, 0)], 0)]:
         assert selftest_exchange(0, world, n_local, pairs, slice_mask) == 0, (world, n_local, pairs, slice_mask)
+
+
+def test_checkpoint_roundtrip_and_zero_copy_view(Backend, tmp_path):
+    """f3: save_state / load_state restore amplitudes (bit for bit), the qubit map (also after deallocations of non-top
+    qubits, i.e. a non-identity physical layout) and the measurement RNG position; the CUDA-array-interface view aliases
+    the state in HBM"""
+    import torch
+
+    from projectq_b200.backend import DeviceStateView
+
+    rng = np.random.default_rng(8)
+    n = 12
+    gpu, chk = Backend(21), checker(21)
+    ids = [3, 40, 7, 1, 9, 22, 5, 11, 2, 8, 30, 6]
+    for q in ids:
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    wf = rand_state(rng, n)
+    gpu.set_wavefunction(wf, ids)
+    chk.set_wavefunction(warg(chk, wf), ids)
+    for sim in (gpu, chk):  # one draw of the RNG stream, and a deallocation that leaves a hole in the layout
+        bits = sim.measure_qubits([7])
+        sim.deallocate_qubit(7)
+    same(gpu, chk)
+    prefix = str(tmp_path / "ckpt")
+    gpu.save_state(prefix)
+    m = rand_unitary(rng, 2)
+    gpu.apply_controlled_gate(m, [3, 40], [])
+    gpu.measure_qubits([1])  # moves the RNG on and changes the state
+    fresh = Backend(999)
+    fresh.load_state(prefix)
+    same(fresh, chk)
+    assert list(fresh.measure_qubits([9, 22])) == list(chk.measure_qubits([9, 22]))  # same RNG position, same state
+    same(fresh, chk)
+    with pytest.raises(RuntimeError):
+        Backend(1).load_state(str(tmp_path / "missing"))
+    # zero-copy view: writing through the tensor changes what the backend sees
+    view = DeviceStateView(fresh)
+    t = torch.as_tensor(view, device="cuda")
+    assert t.dtype == torch.complex128 and t.numel() == 1 << fresh.num_qubits()
+    before = np.asarray(fresh.cheat()[1]).copy()
+    t.mul_(2.0)
+    torch.cuda.synchronize()
+    assert np.array_equal(np.asarray(fresh.cheat()[1]), 2.0 * before)
+    assert sorted(view.layout) == list(range(fresh.num_qubits()))
+
+
+def test_generic_math_function_is_called_on_every_register_value_like_the_reference(Backend):
+    """The reference calls the Python function of a generic math gate for EVERY control-satisfying basis state, populated
+    or not (simulator.hpp:246-253 has no amplitude test; _cppsim.cpp:33-41), so a function that raises on some register
+    value raises whatever the state is.  The shim evaluates the function once per register value instead of once per basis
+    state — the same set of arguments — so it raises for the same functions, and for total functions the results are
+    identical."""
+    ref = load_ref_cppsim()
+    seen = set()
+
+    def picky(x):
+        seen.add(x[0])
+        if x[0] == 5:
+            raise ValueError("unreachable input")
+        return [(x[0] + 1) % 8]
+
+    sims = [Backend(1)] + ([ref.Simulator(1)] if ref is not None else [])
+    for sim in sims:
+        seen.clear()
+        for q in range(4):
+            sim.allocate_qubit(q)
+        # |0000>: register value 5 is not populated, and still the function is asked about it
+        with pytest.raises(Exception):
+            sim.emulate_math(picky, [[0, 1, 2]], [])
+        assert 5 in seen
+    gpu, chk = Backend(1), checker(1)
+    for q in range(5):
+        gpu.allocate_qubit(q)
+        chk.allocate_qubit(q)
+    wf = rand_state(np.random.default_rng(2), 5)
+    gpu.set_wavefunction(wf, list(range(5)))
+    chk.set_wavefunction(warg(chk, wf), list(range(5)))
+    f = lambda x: [(3 * x[0] + 1) % 8, x[1] ^ 1]  # noqa: E731
+    gpu.emulate_math(f, [[0, 1, 2], [4]], [3])
+    chk.emulate_math(f, [[0, 1, 2], [4]], [3])
+    m1, v1 = gpu.cheat()
+    assert np.array_equal(np.asarray(v1), np.asarray(chk.cheat()[1]))
