@@ -50,13 +50,13 @@ Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
     }
     if (device_ < 0 || device_ >= count) throw CudaErr("pqb_create: CUDA device ordinal out of range");
     PQB_CHECK(cudaSetDevice(device_));
-    cudaDeviceProp prop;
-    PQB_CHECK(cudaGetDeviceProperties(&prop, device_));
-    sm_count_ = prop.multiProcessorCount;
+    // (cudaGetDeviceProperties takes milliseconds; small circuits create engines often)
+    PQB_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     PQB_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     PQB_CHECK(cudaEventCreate(&ev0_));
     PQB_CHECK(cudaEventCreate(&ev1_));
-    for (auto& b : buf_) b.init(device_, /*exportable=*/world_ > 1);
+    // only the state buffer reserves its address range now; the two scratch buffers do so on first use (ensure_scratch)
+    state_->init(device_, /*exportable=*/world_ > 1);
     PQB_CHECK(cudaMalloc(&d_partials_, sizeof(double) * k::kReducePartials));
     PQB_CHECK(cudaMalloc(&d_scalars_, sizeof(double) * kScalarDoubles));
     PQB_CHECK(cudaMallocHost(&h_pinned_, sizeof(double) * kScalarDoubles));
@@ -223,6 +223,7 @@ void Engine::reset_stats() {
 double Engine::allreduce_sum(double v) { return dist_ ? dist_->allreduce_sum(v) : v; }
 
 void Engine::ensure_scratch(GrowBuffer& b, size_t bytes) {
+    b.init(device_, /*exportable=*/world_ > 1);  // no-op after the first time
     try {
         b.ensure(bytes, stream_);
     } catch (const std::bad_alloc&) {
@@ -1315,6 +1316,7 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
         bool first_chunk = true;
         do {
             k::PauliTileArgs a = base;
+            a.all_real = 1;
             for (; at_g < generic.size() && a.n_terms < k::kTileTerms; ++at_g) {
                 const k::PauliTerm& tm = terms[generic[at_g]];
                 a.coef[a.n_terms] = make_double2(tm.cre, tm.cim);
@@ -1322,6 +1324,7 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
                 a.zl[a.n_terms] = uint32_t(extract_bits(tm.zmask, base.tile_pos, T));
                 a.z_out[a.n_terms] = tm.zmask & ~S;
                 if (a.zl[a.n_terms] != 0) a.any_zl = 1;
+                if (tm.cim != 0.0) a.all_real = 0;
                 ++a.n_terms;
             }
             for (; at_o < outside.size() && a.n_outside < k::kTileTerms; ++at_o) {

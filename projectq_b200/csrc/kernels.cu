@@ -1177,28 +1177,34 @@ void pauli_apply(const Ctx& c, const double2* in, double2* out, uint64_t n_amps,
 }
 
 // ---- tiled Pauli operators --------------------------------------------------------------------------------------------
+// Every thread owns kTileElems amplitudes of the tile (tile coordinates e * THREADS + tid) and keeps their partial sums in
+// registers; the terms are the outer loop, so a term's coefficient and xmask are fetched once per thread and the inner
+// loop is one XOR, one 128-bit shared load and 2-4 DFMA per amplitude.
+constexpr int kTileElems = 8;  // 2^kTileBits / 256 threads
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
-                                                             double2* __restrict__ acc,
-                                                             const __grid_constant__ PauliTileArgs a,
-                                                             double* __restrict__ partials) {
+__global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
+                                                                double2* __restrict__ acc,
+                                                                const __grid_constant__ PauliTileArgs a,
+                                                                double* __restrict__ partials) {
     extern __shared__ double2 tile[];
     __shared__ double2 coef_s[kTileTerms];  // coefficients with this tile's outside-z sign applied
     __shared__ double2 w_out_s;             // sum of the outside-only diagonal terms for this tile
-    const int tile_amps = 1 << a.T;
+    __shared__ uint64_t goff_s[kTileElems]; // index bits contributed by the element number e (the same for every thread)
+    const uint32_t tile_amps = 1u << a.T;
     constexpr int LOG_THREADS = THREADS == 256 ? 8 : 7;
-    // index bits of this thread's elements that do not depend on the tile: element e of the thread has tile coordinate
-    // t = e * THREADS + tid, whose low bits are tid
-    const int n_e = tile_amps > THREADS ? tile_amps / THREADS : 1;
+    const int n_e = tile_amps > uint32_t(THREADS) ? int(tile_amps / THREADS) : 1;
     auto coord_to_index = [&](uint32_t t) {
         const uint32_t lo_mask = (1u << a.T_lo) - 1;
         return uint64_t(t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
     };
+    if (threadIdx.x < kTileElems) goff_s[threadIdx.x] = coord_to_index((uint32_t(threadIdx.x) << LOG_THREADS) & (tile_amps - 1));
     const uint64_t g_tid = coord_to_index(threadIdx.x & (tile_amps - 1));
+    const bool mine = threadIdx.x < tile_amps;  // tiles smaller than the CTA (tiny states): the other threads idle
     double red = 0.0;
     for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x) {
         const uint64_t base = insert_zero_bits(tid_tile, a.tile_pos, a.T);
-        __syncthreads();  // the previous tile (and its coefficients) is no longer needed
+        __syncthreads();  // the previous tile (and its coefficients) is no longer needed; goff_s is written
         if (int(threadIdx.x) < a.n_terms) {
             double2 c = a.coef[threadIdx.x];
             if (__popcll(base & a.z_out[threadIdx.x]) & 1) c = make_double2(-c.x, -c.y);
@@ -1213,62 +1219,99 @@ __global__ void __launch_bounds__(THREADS) pauli_tile_kernel(const double2* __re
             }
             w_out_s = make_double2(wr, wi);
         }
-        for (int e = 0; e < n_e; ++e) {
-            const uint32_t t = uint32_t(e) * THREADS + threadIdx.x;
-            if (t < uint32_t(tile_amps)) tile[t] = in[base | g_tid | coord_to_index(uint32_t(e) << LOG_THREADS)];
-        }
+        const uint64_t g0 = base | g_tid;
+#pragma unroll
+        for (int e = 0; e < kTileElems; ++e)
+            if (e < n_e && mine) tile[e * THREADS + threadIdx.x] = in[g0 | goff_s[e]];
         __syncthreads();
+        // diagonal part: (table of in-tile terms + per-tile scalar) * psi_j
+        double re[kTileElems], im[kTileElems];
         const double2 w_out = w_out_s;
-        for (int e = 0; e < n_e; ++e) {
-            const uint32_t t = uint32_t(e) * THREADS + threadIdx.x;
-            if (t >= uint32_t(tile_amps)) break;
-            const double2 self = tile[t];
-            // diagonal part: (table of in-tile terms + per-tile scalar) * psi_j
-            double wr = w_out.x, wi = w_out.y;
-            if (a.w_in != nullptr) {
-                const double2 w = __ldg(a.w_in + t);
-                wr += w.x;
-                wi += w.y;
+#pragma unroll
+        for (int e = 0; e < kTileElems; ++e) {
+            re[e] = im[e] = 0.0;
+            if (e < n_e && mine) {
+                const uint32_t t = e * THREADS + threadIdx.x;
+                const double2 self = tile[t];
+                double wr = w_out.x, wi = w_out.y;
+                if (a.w_in != nullptr) {
+                    const double2 w = __ldg(a.w_in + t);
+                    wr += w.x;
+                    wi += w.y;
+                }
+                re[e] = wr * self.x - wi * self.y;
+                im[e] = wr * self.y + wi * self.x;
             }
-            double re = wr * self.x - wi * self.y, im = wr * self.y + wi * self.x;
+        }
+        if (mine) {
             if (a.any_zl) {
-#pragma unroll 2
                 for (int k = 0; k < a.n_terms; ++k) {
-                    const uint32_t s = t ^ a.xl[k];
-                    const double2 v = tile[s];
-                    double2 c = coef_s[k];
-                    if (__popc(s & a.zl[k]) & 1) c = make_double2(-c.x, -c.y);
-                    re = fma(c.x, v.x, re);
-                    re = fma(-c.y, v.y, re);
-                    im = fma(c.x, v.y, im);
-                    im = fma(c.y, v.x, im);
-                }
-            } else {  // pure X strings (every term of a transverse field): no per-amplitude signs
-#pragma unroll 4
-                for (int k = 0; k < a.n_terms; ++k) {
-                    const double2 v = tile[t ^ a.xl[k]];
+                    const uint32_t xl = a.xl[k], zl = a.zl[k];
                     const double2 c = coef_s[k];
-                    re = fma(c.x, v.x, re);
-                    re = fma(-c.y, v.y, re);
-                    im = fma(c.x, v.y, im);
-                    im = fma(c.y, v.x, im);
+#pragma unroll
+                    for (int e = 0; e < kTileElems; ++e) {
+                        if (e < n_e) {
+                            const uint32_t s = (e * THREADS + threadIdx.x) ^ xl;
+                            const double2 v = tile[s];
+                            const bool neg = __popc(s & zl) & 1;
+                            const double cx = neg ? -c.x : c.x, cy = neg ? -c.y : c.y;
+                            re[e] = fma(cx, v.x, re[e]);
+                            re[e] = fma(-cy, v.y, re[e]);
+                            im[e] = fma(cx, v.y, im[e]);
+                            im[e] = fma(cy, v.x, im[e]);
+                        }
+                    }
+                }
+            } else if (a.all_real) {  // real coefficients on pure X strings (a transverse field): 2 DFMA per amplitude and term
+                for (int k = 0; k < a.n_terms; ++k) {
+                    const uint32_t xl = a.xl[k];
+                    const double cx = coef_s[k].x;
+#pragma unroll
+                    for (int e = 0; e < kTileElems; ++e) {
+                        if (e < n_e) {
+                            const double2 v = tile[(e * THREADS + threadIdx.x) ^ xl];
+                            re[e] = fma(cx, v.x, re[e]);
+                            im[e] = fma(cx, v.y, im[e]);
+                        }
+                    }
+                }
+            } else {
+                for (int k = 0; k < a.n_terms; ++k) {
+                    const uint32_t xl = a.xl[k];
+                    const double2 c = coef_s[k];
+#pragma unroll
+                    for (int e = 0; e < kTileElems; ++e) {
+                        if (e < n_e) {
+                            const double2 v = tile[(e * THREADS + threadIdx.x) ^ xl];
+                            re[e] = fma(c.x, v.x, re[e]);
+                            re[e] = fma(-c.y, v.y, re[e]);
+                            im[e] = fma(c.x, v.y, im[e]);
+                            im[e] = fma(c.y, v.x, im[e]);
+                        }
+                    }
                 }
             }
+        }
+#pragma unroll
+        for (int e = 0; e < kTileElems; ++e) {
+            if (!(e < n_e && mine)) continue;
             if (a.expectation) {
-                red += self.x * re + self.y * im;  // Re(conj(psi_j) s_j)
+                const double2 self = tile[e * THREADS + threadIdx.x];
+                red += self.x * re[e] + self.y * im[e];  // Re(conj(psi_j) s_j)
                 continue;
             }
-            const uint64_t g = base | g_tid | coord_to_index(uint32_t(e) << LOG_THREADS);
+            const uint64_t g = g0 | goff_s[e];
+            double sr = re[e], si = im[e];
             if (!a.first) {
                 const double2 prev = u[g];
-                re += prev.x;
-                im += prev.y;
+                sr += prev.x;
+                si += prev.y;
             }
             if (!a.final) {
-                u[g] = make_double2(re, im);
+                u[g] = make_double2(sr, si);
                 continue;
             }
-            const double ore = re * a.sre - im * a.sim, oim = re * a.sim + im * a.sre;
+            const double ore = sr * a.sre - si * a.sim, oim = sr * a.sim + si * a.sre;
             u[g] = make_double2(ore, oim);
             if (acc != nullptr && (g & a.cmask) == a.cmask) {
                 const double2 o = acc[g];
@@ -1284,7 +1327,7 @@ __global__ void __launch_bounds__(THREADS) pauli_tile_kernel(const double2* __re
 }
 
 int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs& a, double* d_partials) {
-    if (a.T > 12 || a.T < 0 || a.n_terms > kTileTerms || a.n_outside > kTileTerms)
+    if (a.T > kTileBits || a.T < 0 || a.n_terms > kTileTerms || a.n_outside > kTileTerms)
         throw std::invalid_argument("pauli_tile_pass: bad arguments");
     constexpr int THREADS = 256;
     const size_t smem = sizeof(double2) << a.T;
@@ -1294,7 +1337,7 @@ int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, c
         configured = true;
     }
     uint64_t grid = a.n_tiles;
-    if (grid > 148 * 6) grid = 148 * 6;  // 6 resident 32 KB tiles per SM
+    if (grid > 148 * 4) grid = 148 * 4;  // 4 resident CTAs per SM (32 KB of shared memory and <= 64 registers per thread each)
     const bool reduce = a.expectation || (a.final && acc != nullptr);
     pauli_tile_kernel<THREADS><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
     launched(c);

@@ -157,6 +157,7 @@ struct PauliTileArgs {
     uint32_t zl[kTileTerms];        // z bits inside the tile, in tile coordinates
     int n_terms;
     int any_zl;                     // 0: no term of this launch has z bits inside the tile (no per-amplitude signs)
+    int all_real;                   // 1: every coefficient of this launch is real
     double2 coef_outside[kTileTerms];  // diagonal terms with z entirely outside the tile
     uint64_t z_outside[kTileTerms];
     int n_outside;

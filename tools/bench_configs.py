@@ -53,6 +53,8 @@ for name, seed in (("qft20", 1), ("shor4087", 3)):
 def through_main_engine():
     from tests import refenv
 
+    if ref is not None:  # the compiled reference is already loaded (a pybind11 module cannot be loaded twice)
+        sys.modules.setdefault("projectq.backends._sim._cppsim", ref)
     if refenv.import_projectq("reference") is None:
         emit({"config": "MainEngine legs", "unavailable": "reference front end not staged (baseline/_ref)"})
         return
