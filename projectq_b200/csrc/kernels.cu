@@ -1182,29 +1182,57 @@ void pauli_apply(const Ctx& c, const double2* in, double2* out, uint64_t n_amps,
 // loop is one XOR, one 128-bit shared load and 2-4 DFMA per amplitude.
 constexpr int kTileElems = 8;  // 2^kTileBits / 256 threads
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// FULL: the tile has exactly kTileElems * THREADS amplitudes (every state of kTileBits or more local bits), so the element
+// loops carry no guards; the other instantiation serves tiny states.  Shared memory is addressed through 32-bit shared
+// addresses (ld.shared): with generic pointers the compiler re-derived the shared window for every load.
+template <int THREADS, bool FULL>
+__global__ void __launch_bounds__(THREADS, 3) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
                                                                 double2* __restrict__ acc,
                                                                 const __grid_constant__ PauliTileArgs a,
                                                                 double* __restrict__ partials) {
-    extern __shared__ double2 tile[];
+    extern __shared__ double2 tile_buffers[];  // two tiles: the next one streams in (cp.async) while this one is used
     __shared__ double2 coef_s[kTileTerms];  // coefficients with this tile's outside-z sign applied
     __shared__ double2 w_out_s;             // sum of the outside-only diagonal terms for this tile
     __shared__ uint64_t goff_s[kTileElems]; // index bits contributed by the element number e (the same for every thread)
     const uint32_t tile_amps = 1u << a.T;
     constexpr int LOG_THREADS = THREADS == 256 ? 8 : 7;
-    const int n_e = tile_amps > uint32_t(THREADS) ? int(tile_amps / THREADS) : 1;
+    const int n_e = FULL ? kTileElems : (tile_amps > uint32_t(THREADS) ? int(tile_amps / THREADS) : 1);
     auto coord_to_index = [&](uint32_t t) {
         const uint32_t lo_mask = (1u << a.T_lo) - 1;
         return uint64_t(t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
     };
     if (threadIdx.x < kTileElems) goff_s[threadIdx.x] = coord_to_index((uint32_t(threadIdx.x) << LOG_THREADS) & (tile_amps - 1));
     const uint64_t g_tid = coord_to_index(threadIdx.x & (tile_amps - 1));
-    const bool mine = threadIdx.x < tile_amps;  // tiles smaller than the CTA (tiny states): the other threads idle
+    const bool mine = FULL || threadIdx.x < tile_amps;  // tiles smaller than the CTA (tiny states): the other threads idle
+    const uint32_t buffers_s = smem_addr(tile_buffers), t16 = threadIdx.x * 16;
+    __syncthreads();                            // goff_s
+    // asynchronous copy of one tile into one of the two buffers (16 bytes per thread and element, L2 -> shared directly)
+    auto fetch = [&](uint64_t tile_id, int buf) {
+        const uint64_t g0f = insert_zero_bits(tile_id, a.tile_pos, a.T) | g_tid;
+        double2* dst = tile_buffers + size_t(buf) * tile_amps;
+#pragma unroll
+        for (int e = 0; e < kTileElems; ++e)
+            if ((FULL || e < n_e) && mine)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + e * THREADS + threadIdx.x)),
+                             "l"(in + (g0f | goff_s[e]))
+                             : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     double red = 0.0;
-    for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x) {
+    int buf = 0;
+    if (uint64_t(blockIdx.x) < a.n_tiles) fetch(blockIdx.x, 0);
+    for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x, buf ^= 1) {
         const uint64_t base = insert_zero_bits(tid_tile, a.tile_pos, a.T);
-        __syncthreads();  // the previous tile (and its coefficients) is no longer needed; goff_s is written
+        const uint32_t tile_s = buffers_s + uint32_t(buf) * (tile_amps * 16);  // shared address of this tile
+        auto at = [&](int e, uint32_t x16) { return lds_d2(tile_s + ((uint32_t(e) * (THREADS * 16) + t16) ^ x16)); };
+        const bool more = tid_tile + gridDim.x < a.n_tiles;
+        if (more) fetch(tid_tile + gridDim.x, buf ^ 1);  // the other buffer was released by the barrier that ended the last tile
         if (int(threadIdx.x) < a.n_terms) {
             double2 c = a.coef[threadIdx.x];
             if (__popcll(base & a.z_out[threadIdx.x]) & 1) c = make_double2(-c.x, -c.y);
@@ -1219,20 +1247,21 @@ __global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* _
             }
             w_out_s = make_double2(wr, wi);
         }
-        const uint64_t g0 = base | g_tid;
-#pragma unroll
-        for (int e = 0; e < kTileElems; ++e)
-            if (e < n_e && mine) tile[e * THREADS + threadIdx.x] = in[g0 | goff_s[e]];
+        if (more)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile has landed (the next one may still be in flight)
+        else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        const uint64_t g0 = base | g_tid;
         // diagonal part: (table of in-tile terms + per-tile scalar) * psi_j
         double re[kTileElems], im[kTileElems];
         const double2 w_out = w_out_s;
 #pragma unroll
         for (int e = 0; e < kTileElems; ++e) {
             re[e] = im[e] = 0.0;
-            if (e < n_e && mine) {
+            if ((FULL || e < n_e) && mine) {
                 const uint32_t t = e * THREADS + threadIdx.x;
-                const double2 self = tile[t];
+                const double2 self = at(e, 0);
                 double wr = w_out.x, wi = w_out.y;
                 if (a.w_in != nullptr) {
                     const double2 w = __ldg(a.w_in + t);
@@ -1250,9 +1279,9 @@ __global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* _
                     const double2 c = coef_s[k];
 #pragma unroll
                     for (int e = 0; e < kTileElems; ++e) {
-                        if (e < n_e) {
+                        if (FULL || e < n_e) {
                             const uint32_t s = (e * THREADS + threadIdx.x) ^ xl;
-                            const double2 v = tile[s];
+                            const double2 v = at(e, xl << 4);
                             const bool neg = __popc(s & zl) & 1;
                             const double cx = neg ? -c.x : c.x, cy = neg ? -c.y : c.y;
                             re[e] = fma(cx, v.x, re[e]);
@@ -1264,12 +1293,12 @@ __global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* _
                 }
             } else if (a.all_real) {  // real coefficients on pure X strings (a transverse field): 2 DFMA per amplitude and term
                 for (int k = 0; k < a.n_terms; ++k) {
-                    const uint32_t xl = a.xl[k];
+                    const uint32_t x16 = a.xl[k] << 4;
                     const double cx = coef_s[k].x;
 #pragma unroll
                     for (int e = 0; e < kTileElems; ++e) {
-                        if (e < n_e) {
-                            const double2 v = tile[(e * THREADS + threadIdx.x) ^ xl];
+                        if (FULL || e < n_e) {
+                            const double2 v = at(e, x16);
                             re[e] = fma(cx, v.x, re[e]);
                             im[e] = fma(cx, v.y, im[e]);
                         }
@@ -1277,12 +1306,12 @@ __global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* _
                 }
             } else {
                 for (int k = 0; k < a.n_terms; ++k) {
-                    const uint32_t xl = a.xl[k];
+                    const uint32_t x16 = a.xl[k] << 4;
                     const double2 c = coef_s[k];
 #pragma unroll
                     for (int e = 0; e < kTileElems; ++e) {
-                        if (e < n_e) {
-                            const double2 v = tile[(e * THREADS + threadIdx.x) ^ xl];
+                        if (FULL || e < n_e) {
+                            const double2 v = at(e, x16);
                             re[e] = fma(c.x, v.x, re[e]);
                             re[e] = fma(-c.y, v.y, re[e]);
                             im[e] = fma(c.x, v.y, im[e]);
@@ -1294,9 +1323,9 @@ __global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* _
         }
 #pragma unroll
         for (int e = 0; e < kTileElems; ++e) {
-            if (!(e < n_e && mine)) continue;
+            if (!((FULL || e < n_e) && mine)) continue;
             if (a.expectation) {
-                const double2 self = tile[e * THREADS + threadIdx.x];
+                const double2 self = at(e, 0);
                 red += self.x * re[e] + self.y * im[e];  // Re(conj(psi_j) s_j)
                 continue;
             }
@@ -1319,6 +1348,7 @@ __global__ void __launch_bounds__(THREADS, 4) pauli_tile_kernel(const double2* _
                 red += ore * ore + oim * oim;
             }
         }
+        __syncthreads();  // everybody is done with this buffer and with coef_s / w_out_s
     }
     if (partials != nullptr) {
         red = block_sum(red);
@@ -1330,16 +1360,20 @@ int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, c
     if (a.T > kTileBits || a.T < 0 || a.n_terms > kTileTerms || a.n_outside > kTileTerms)
         throw std::invalid_argument("pauli_tile_pass: bad arguments");
     constexpr int THREADS = 256;
-    const size_t smem = sizeof(double2) << a.T;
+    const size_t smem = 2 * (sizeof(double2) << a.T);  // double-buffered tile
     static bool configured = false;
     if (!configured) {
-        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         configured = true;
     }
     uint64_t grid = a.n_tiles;
-    if (grid > 148 * 4) grid = 148 * 4;  // 4 resident CTAs per SM (32 KB of shared memory and <= 64 registers per thread each)
+    if (grid > 148 * 3) grid = 148 * 3;  // 3 resident CTAs per SM (64 KB of shared memory and <= 64 registers per thread each)
     const bool reduce = a.expectation || (a.final && acc != nullptr);
-    pauli_tile_kernel<THREADS><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+    if (a.T == kTileBits)
+        pauli_tile_kernel<THREADS, true><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+    else
+        pauli_tile_kernel<THREADS, false><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
     launched(c);
     return int(grid);
 }
