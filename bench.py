@@ -465,13 +465,20 @@ def run_ours(args):
 
     extras = {}
     if not args.no_extra_legs:
-        if n != 33:
-            extras["strong_33q"] = extra_leg(pl, 33, 3, 2)
-        if world == 8:
-            extras["weak_36q"] = extra_leg(pl, 36, 3, 2)
+        legs = ([("strong_33q", 33)] if n != 33 else []) + ([("weak_36q", 36)] if world == 8 else [])
+        for key, qubits in legs:
+            try:
+                extras[key] = extra_leg(pl, qubits, 3, 2)
+            except (RuntimeError, MemoryError) as exc:  # e.g. not enough free HBM for a 128 GiB shard: the headline stands
+                if world > 1:
+                    raise  # the other ranks are inside collectives: fail loudly rather than hang
+                extras[key] = {"unavailable": str(exc)[:300]}
     me = None
     if world == 1 and not args.no_main_engine:
-        me = main_engine_leg(n, max(1, min(args.steps, 3)))
+        try:
+            me = main_engine_leg(n, max(1, min(args.steps, 3)))
+        except Exception as exc:  # the front end is the reference's code: report, do not lose the line
+            me = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
 
     if rank != 0:
         return
