@@ -225,6 +225,12 @@ PQB_API int pqb_host_fdpass_selftest(uint64_t run_tag, int rank, int world);
  * for each partner rank the pattern of exchanged local bits of the sub-block swapped with it */
 PQB_API int pqb_host_plan_exchange(int rank, const int32_t* pairs, size_t n_pairs, int32_t* out_peers, uint64_t* out_patterns,
                                    size_t cap, size_t* out_n);
+/* planner of the tiled Pauli-operator kernels (engine.h plan_pauli_tiles): for terms given by their x/z masks over
+ * n_local_bits index bits, which launch applies each term (-1: no tile can hold its X/Y support, it goes through global
+ * gathers) and the tile bits of every launch */
+PQB_API int pqb_host_plan_pauli_tiles(const uint64_t* xmasks, const uint64_t* zmasks, size_t n_terms, int n_local_bits,
+                                      int32_t* out_launch_of_term, uint64_t* out_tile_masks, size_t cap_launches,
+                                      size_t* out_n_launches);
 /* a fresh 128-byte ncclUniqueId (rank 0 creates it, the launcher's plumbing broadcasts it to the other ranks) */
 PQB_API int pqb_nccl_unique_id(void* out128);
 /* library version string */

@@ -1261,16 +1261,9 @@ static void to_physical(std::vector<k::PauliTerm>& terms, const std::vector<uint
 // in runs of at least 64 bytes) plus the bits that the most still-uncovered terms need; a term is applied by the first
 // launch whose tile bits contain its whole xmask (z factors are signs and never need a partner amplitude).  Terms whose
 // support is too large for any tile are returned in `wide` and go through per-term global gathers.
-struct PauliPlan {
-    std::vector<k::PauliTileArgs> launches;  // in execution order; first/final/scale are filled in by the caller
-    std::vector<long> table_at;              // per launch: offset of its diagonal table in `tables`, or -1
-    std::vector<double2> tables;             // 2^T entries per table
-    std::vector<k::PauliTerm> wide;
-    const k::PauliTerm* d_wide = nullptr;
-};
-
-static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
+PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
     PauliPlan plan;
+    plan.launch_of_term.assign(terms.size(), -1);
     const int T = std::min(k::kTileBits, L);
     const uint64_t low2 = L >= 2 ? 3 : (L == 1 ? 1 : 0);
     std::vector<int> todo;
@@ -1299,6 +1292,7 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
             if (tm.xmask != 0) {
                 generic.push_back(i);
             } else if ((tm.zmask & ~S) == 0) {
+                plan.launch_of_term[i] = int(plan.launches.size());  // the table travels with the first launch of this set
                 if (table.empty()) table.assign(size_t(1) << T, make_double2(0.0, 0.0));
                 const uint32_t zl = uint32_t(extract_bits(tm.zmask, base.tile_pos, T));
                 for (uint32_t t = 0; t < (1u << T); ++t) {
@@ -1319,6 +1313,7 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
             a.all_real = 1;
             for (; at_g < generic.size() && a.n_terms < k::kTileTerms; ++at_g) {
                 const k::PauliTerm& tm = terms[generic[at_g]];
+                plan.launch_of_term[generic[at_g]] = int(plan.launches.size());
                 a.coef[a.n_terms] = make_double2(tm.cre, tm.cim);
                 a.xl[a.n_terms] = uint32_t(extract_bits(tm.xmask, base.tile_pos, T));
                 a.zl[a.n_terms] = uint32_t(extract_bits(tm.zmask, base.tile_pos, T));
@@ -1329,6 +1324,7 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
             }
             for (; at_o < outside.size() && a.n_outside < k::kTileTerms; ++at_o) {
                 const k::PauliTerm& tm = terms[outside[at_o]];
+                plan.launch_of_term[outside[at_o]] = int(plan.launches.size());
                 a.coef_outside[a.n_outside] = make_double2(tm.cre, tm.cim);
                 a.z_outside[a.n_outside] = tm.zmask;
                 ++a.n_outside;
@@ -1340,6 +1336,7 @@ static PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L)
             }
             plan.launches.push_back(a);
             plan.table_at.push_back(at);
+            plan.tile_mask.push_back(S);
             first_chunk = false;
         } while (at_g < generic.size() || at_o < outside.size());
     };

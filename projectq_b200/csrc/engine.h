@@ -57,7 +57,6 @@ private:
     int prev_ = -1;
 };
 
-struct PauliPlan;  // engine.cpp
 
 struct TermsView {
     size_t n_terms;
@@ -67,6 +66,20 @@ struct TermsView {
     const double* coeff;  // real: n_terms, complex: 2*n_terms
     bool complex_coeff;
 };
+
+// How a Pauli-string operator is executed (engine.cpp plan_pauli_tiles): a few launches of the tiled kernel, each with its
+// own set of tile bits, plus the terms whose X/Y support no tile can hold.  Pure host logic (CPU-tested through
+// pqb_host_plan_pauli_tiles).
+struct PauliPlan {
+    std::vector<k::PauliTileArgs> launches;  // in execution order; first/final/scale are filled in by the caller
+    std::vector<long> table_at;              // per launch: offset of its diagonal table in `tables`, or -1
+    std::vector<uint64_t> tile_mask;         // per launch: its tile bits
+    std::vector<double2> tables;             // 2^T entries per table
+    std::vector<k::PauliTerm> wide;
+    std::vector<int> launch_of_term;         // per input term: the launch that applies it, -1 = wide
+    const k::PauliTerm* d_wide = nullptr;
+};
+PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int n_local_bits);
 
 class Engine {
 public:

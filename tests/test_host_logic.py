@@ -311,3 +311,45 @@ def test_descriptor_channel_between_four_processes(lib):
     for p in procs:
         p.join(timeout=30)
     assert results == {0: 0, 1: 0, 2: 0, 3: 0}
+
+
+def plan_tiles(lib, xmasks, zmasks, n_bits):
+    n = len(xmasks)
+    xs = (ctypes.c_uint64 * n)(*xmasks)
+    zs = (ctypes.c_uint64 * n)(*zmasks)
+    launch = (ctypes.c_int32 * n)()
+    masks = (ctypes.c_uint64 * 256)()
+    n_launch = ctypes.c_size_t()
+    st = lib.pqb_host_plan_pauli_tiles(xs, zs, ctypes.c_size_t(n), ctypes.c_int(n_bits), launch, masks, ctypes.c_size_t(256),
+                                       ctypes.byref(n_launch))
+    assert st == 0
+    return list(launch), [masks[i] for i in range(n_launch.value)]
+
+
+def test_pauli_tile_planner_covers_every_term_once(lib):
+    """every term is applied by exactly one launch whose tile bits contain its whole X/Y support (or is declared wide), a
+    tile never has more than 11 bits, and the 28-qubit TFIM needs 3 tile-bit sets"""
+    n = 28
+    xm = [0] * (n - 1) + [1 << i for i in range(n)]
+    zm = [(1 << i) | (1 << (i + 1)) for i in range(n - 1)] + [0] * n
+    launch, masks = plan_tiles(lib, xm, zm, n)
+    assert len(masks) == 3 and all(bin(m).count("1") == 11 for m in masks)
+    for x, l in zip(xm, launch):
+        assert 0 <= l < len(masks) and (x & ~masks[l]) == 0
+    # random strings, some wider than a tile, more than 64 per set (several launches share one set of tile bits)
+    rng = np.random.default_rng(9)
+    n = 20
+    xm, zm = [], []
+    for _ in range(300):
+        w = int(rng.integers(0, 6))
+        xm.append(int(sum(1 << int(q) for q in rng.permutation(n)[:w])))
+        zm.append(int(rng.integers(0, 1 << n)))
+    xm += [(1 << 13) - 1, ((1 << 14) - 1) << 3]  # 13 and 14 flipped qubits: no 11-bit tile holds them
+    zm += [0, 5]
+    launch, masks = plan_tiles(lib, xm, zm, n)
+    assert launch[-1] == -1 and launch[-2] == -1
+    for x, l in zip(xm[:-2], launch[:-2]):
+        assert 0 <= l < len(masks) and (x & ~masks[l]) == 0 and bin(masks[l]).count("1") <= 11
+    # a state smaller than a tile: one launch, every bit a tile bit
+    launch, masks = plan_tiles(lib, [1, 6, 0], [0, 1, 7], 3)
+    assert masks == [7] and launch == [0, 0, 0]
