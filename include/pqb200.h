@@ -157,7 +157,8 @@ PQB_API int pqb_apply_gate_stream(pqb_sim* sim, const void* packed, size_t n_byt
  * Checkpoint of the (possibly sharded) state.  Every rank writes / reads its own file "<prefix>.rank<r>of<w>.pqbs": a
  * header (qubit ids and positions, physical layout, RNG stream position) followed by the shard's amplitudes exactly as they
  * lie in HBM — nothing is gathered or re-laid-out, so a 36-qubit state (1.1 TB over 8 ranks) is saved and restored shard by
- * shard.  Loading needs an engine with the same world size and rank; it replaces the engine's qubits, state and RNG. */
+ * shard.  Loading needs an engine with the same world size and rank; it replaces the engine's qubits, state and RNG (if it
+ * fails half-way the amplitudes are undefined, the bookkeeping is unchanged). */
 PQB_API int pqb_save_state(pqb_sim* sim, const char* path_prefix);
 PQB_API int pqb_load_state(pqb_sim* sim, const char* path_prefix);
 /* Zero-copy view for consumers that can wrap device memory (CUDA array interface / DLPack producers): the device pointer

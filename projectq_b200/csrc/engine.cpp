@@ -797,9 +797,25 @@ void Engine::measure_qubits(const uint32_t* ids, size_t n, uint8_t* out) {
     bool overflowed = false; // the running sum never reached rnd: the reference ends on the last index
     int top = n_;
     if (n_ == 0) top = 0;
+    // The first level sweeps the whole state anyway, so it also bins over the measured positions that lie below its own
+    // bits (when they fit): the norm of the surviving amplitudes is then a sum of first-level bins and the separate norm
+    // sweep before the collapse is not needed.
+    std::vector<double> level1_bins;
+    std::vector<int> level1_bits;  // logical position of every bit of a first-level bin index
     while (top > 0) {
         const int m = std::min(kBinBits, top);
-        const int lo = top - m;  // bins are logical bits [lo, top)
+        const int lo = top - m;  // this level decides logical bits [lo, top)
+        std::vector<int> bin_lp;  // logical positions of the bin-index bits, least significant first
+        if (top == n_) {
+            std::vector<int> extra;
+            for (auto lp : lpos)
+                if (int(lp) < lo && std::find(extra.begin(), extra.end(), int(lp)) == extra.end()) extra.push_back(int(lp));
+            std::sort(extra.begin(), extra.end());
+            if (m + int(extra.size()) <= 12) bin_lp = extra;
+        }
+        const int n_extra = int(bin_lp.size());
+        for (int lp = lo; lp < top; ++lp) bin_lp.push_back(lp);
+        const int n_bin_bits = int(bin_lp.size());
         const int n_bins = 1 << m;
         // local view: decided bits and bin bits that live on local physical bits
         std::vector<uint8_t> ins;
@@ -808,8 +824,8 @@ void Engine::measure_qubits(const uint32_t* ids, size_t n, uint8_t* out) {
         uint64_t fixed_val = 0;
         bool rank_matches_prefix = true;
         int bin_is_local[16];
-        for (int b = 0; b < m; ++b) {
-            const int lp = lo + b;
+        for (int b = 0; b < n_bin_bits; ++b) {
+            const int lp = bin_lp[b];
             bin_is_local[b] = is_local(lp);
             if (bin_is_local[b]) {
                 bin_pos[m_local++] = loc_[lp];
@@ -826,7 +842,7 @@ void Engine::measure_qubits(const uint32_t* ids, size_t n, uint8_t* out) {
         }
         if (dist_ && (uint64_t(rank_) & dist_->free_rank_bits_mask()) != 0) rank_matches_prefix = false;
         std::sort(ins.begin(), ins.end());
-        std::vector<double> bins(n_bins, 0.0);
+        std::vector<double> fine(size_t(1) << n_bin_bits, 0.0);
         if (rank_matches_prefix) {
             k::bin_sums(ctx(), psi(), L_, int(ins.size()), ins.data(), fixed_val, m_local, bin_pos, d_partials_, d_scalars_);
             PQB_CHECK(cudaMemcpyAsync(h_pinned_, d_scalars_, sizeof(double) << m_local, cudaMemcpyDeviceToHost, stream_));
@@ -834,18 +850,25 @@ void Engine::measure_qubits(const uint32_t* ids, size_t n, uint8_t* out) {
             // scatter the local bins into the full bin array (rank bits of this rank fill the non-local bin bits)
             for (int lb = 0; lb < (1 << m_local); ++lb) {
                 int full = 0, j = 0;
-                for (int b = 0; b < m; ++b) {
+                for (int b = 0; b < n_bin_bits; ++b) {
                     int bit;
                     if (bin_is_local[b])
                         bit = (lb >> j++) & 1;
                     else
-                        bit = (rank_ >> (loc_[lo + b] - 64)) & 1;
+                        bit = (rank_ >> (loc_[bin_lp[b]] - 64)) & 1;
                     full |= bit << b;
                 }
-                bins[full] = h_pinned_[lb];
+                fine[full] = h_pinned_[lb];
             }
         }
-        if (dist_) dist_->allreduce_sum_vec(bins.data(), n_bins);
+        if (dist_) dist_->allreduce_sum_vec(fine.data(), fine.size());
+        // the walk is over the bits this level decides: sum the extra (measured, lower) bits out
+        std::vector<double> bins(n_bins, 0.0);
+        for (size_t f = 0; f < fine.size(); ++f) bins[f >> n_extra] += fine[f];
+        if (top == n_) {
+            level1_bins.swap(fine);
+            level1_bits = bin_lp;
+        }
         // sequential walk (while (P < rnd && pick < size) P += ...; pick--)
         int chosen = -1;
         double before = 0.0;
@@ -891,11 +914,26 @@ void Engine::measure_qubits(const uint32_t* ids, size_t n, uint8_t* out) {
     uint64_t lmask, lval;
     const bool mine = split_mask(mask, val, &lmask, &lval);
     double kept = 0.0;
-    if (mine) {
-        k::norm_masked(ctx(), psi(), local_amps(), lmask, lval, d_partials_, d_scalars_);
-        kept = read_scalar(d_scalars_);
+    bool from_bins = !level1_bins.empty();
+    for (size_t i = 0; i < n && from_bins; ++i)
+        if (std::find(level1_bits.begin(), level1_bits.end(), int(lpos[i])) == level1_bits.end()) from_bins = false;
+    if (from_bins) {
+        // every measured position is a bit of the first-level bin index: the surviving norm is the sum of the matching bins
+        uint64_t bmask = 0, bval = 0;
+        for (size_t b = 0; b < level1_bits.size(); ++b)
+            if ((mask >> level1_bits[b]) & 1) {
+                bmask |= uint64_t(1) << b;
+                bval |= ((val >> level1_bits[b]) & 1) << b;
+            }
+        for (size_t f = 0; f < level1_bins.size(); ++f)
+            if ((f & bmask) == bval) kept += level1_bins[f];
+    } else {
+        if (mine) {
+            k::norm_masked(ctx(), psi(), local_amps(), lmask, lval, d_partials_, d_scalars_);
+            kept = read_scalar(d_scalars_);
+        }
+        kept = allreduce_sum(kept);
     }
-    kept = allreduce_sum(kept);
     const double scale = 1.0 / std::sqrt(kept);
     if (mine)
         k::collapse_scale(ctx(), psi(), local_amps(), lmask, lval, scale);

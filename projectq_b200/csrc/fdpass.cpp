@@ -2,6 +2,7 @@
 #include "fdpass.h"
 
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -46,6 +47,7 @@ void read_all(int fd, void* p, size_t n) {
         const ssize_t r = ::recv(fd, c, n, 0);
         if (r < 0) {
             if (errno == EINTR) continue;
+            if (errno == EAGAIN || errno == EWOULDBLOCK) throw std::runtime_error("fdpass: the partner rank did not answer in time");
             fail("recv");
         }
         if (r == 0) throw std::runtime_error("fdpass: peer closed the connection");
@@ -55,6 +57,14 @@ void read_all(int fd, void* p, size_t n) {
 }
 
 constexpr size_t kMaxFdsPerMsg = 32;
+
+// a partner that died must not leave this rank blocked forever: give every connected socket a receive time limit
+void set_receive_timeout(int fd) {
+    timeval tv;
+    tv.tv_sec = 300;
+    tv.tv_usec = 0;
+    ::setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+}
 
 }  // namespace
 
@@ -97,6 +107,7 @@ int FdChannel::socket_to(int peer) {
             std::this_thread::sleep_for(std::chrono::milliseconds(10));
         }
         if (fd < 0) throw std::runtime_error("fdpass: partner rank is not listening");
+        set_receive_timeout(fd);
         const int32_t me = rank_;
         write_all(fd, &me, sizeof(me));
         conn_[peer] = fd;
@@ -116,6 +127,7 @@ int FdChannel::socket_to(int peer) {
             ::close(fd);
             continue;
         }
+        set_receive_timeout(fd);
         int32_t who = -1;
         read_all(fd, &who, sizeof(who));
         // a rank connects only to lower ranks, and only once
@@ -179,6 +191,8 @@ void FdChannel::recv(int peer, void* payload, size_t n_bytes, std::vector<int>& 
         if (r == ssize_t(sizeof(header))) break;
         if (r < 0 && errno == EINTR) continue;
         if (r == 0) throw std::runtime_error("fdpass: peer closed the connection");
+        if (r < 0 && (errno == EAGAIN || errno == EWOULDBLOCK))
+            throw std::runtime_error("fdpass: the partner rank did not answer in time");
         fail("recvmsg");
     }
     fds.clear();
