@@ -646,6 +646,22 @@ bool Dist::sync_mapping(int partner, const GrowBuffer& state, PeerMapping** out)
     return ok;
 }
 
+const double2* Dist::peer_buffer(int partner, const GrowBuffer& mine) {
+    if (!p2p_ok_ || !mine.uses_vmm()) return nullptr;
+    PeerMapping* m = nullptr;
+    std::vector<int> none;
+    uint64_t ok = sync_mapping(partner, mine, &m) ? 1 : 0, theirs = 0;
+    fdchan_->send(partner, &ok, sizeof(ok), {});
+    fdchan_->recv(partner, &theirs, sizeof(theirs), none, 0);
+    return ok && theirs ? m->amps() : nullptr;
+}
+
+void Dist::barrier_on_stream() {
+    ensure_buf(2);
+    nccl_check(nccl().AllReduce(d_buf_, d_buf_ + 1, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(comm_), stream_),
+               "ncclAllReduce(barrier)");
+}
+
 bool Dist::prepare_exchange(const std::vector<std::pair<int, int>>& swaps, const GrowBuffer& state, int device) {
     (void)device;
     if (!p2p_ok_ || swaps.empty() || swaps.size() > 3) return false;

@@ -112,6 +112,12 @@ public:
     // orders it after the passes that precede it (cudaStreamWaitEvent on comm_stream()) and waits for an event recorded
     // behind it before touching the slice again.
     void exchange_slice(const k::Slice& slice, int n_local_bits, int sm_count, uint64_t* bytes_sent);
+    // `partner`'s buffer of the same role as `mine` (the ranks run the same program, so their buffers rotate alike), mapped
+    // into this process; nullptr when peer mapping is not available.  Pairwise collective: the partner calls it with this
+    // rank as its partner.
+    const double2* peer_buffer(int partner, const GrowBuffer& mine);
+    // rendezvous of all ranks on the engine's stream without blocking the host (a one-element all-reduce)
+    void barrier_on_stream();
     cudaStream_t comm_stream() const { return comm_stream_; }
     // non-zero once a cross-GPU wait inside an exchange kernel timed out (the state is then undefined)
     int exchange_error() const { return h_error_ ? *h_error_ : 0; }

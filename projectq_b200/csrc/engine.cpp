@@ -1270,30 +1270,6 @@ std::vector<k::PauliTerm> Engine::build_terms(const TermsView& t, const uint32_t
     return out;
 }
 
-// logical masks -> local physical masks; rank-bit Z factors are folded into the coefficient
-static void to_physical(std::vector<k::PauliTerm>& terms, const std::vector<uint8_t>& loc, int n, int rank) {
-    for (auto& t : terms) {
-        uint64_t x = 0, z = 0;
-        int flip = 0;
-        for (int p = 0; p < n; ++p) {
-            const uint64_t bit = uint64_t(1) << p;
-            if (loc[p] < 64) {
-                if (t.xmask & bit) x |= uint64_t(1) << loc[p];
-                if (t.zmask & bit) z |= uint64_t(1) << loc[p];
-            } else {
-                if (t.xmask & bit) throw RuntimeErr("internal: X on a rank bit was not remapped");
-                if ((t.zmask & bit) && ((rank >> (loc[p] - 64)) & 1)) flip ^= 1;
-            }
-        }
-        t.xmask = x;
-        t.zmask = z;
-        if (flip) {
-            t.cre = -t.cre;
-            t.cim = -t.cim;
-        }
-    }
-}
-
 // ---- tiled execution of a Pauli-string operator (kernels.cuh pauli_tile_pass) -------------------------------------------
 // Cover the X/Y supports of the terms with sets of tile bits.  Every set holds index bits 0 and 1 (so that a tile is read
 // in runs of at least 64 bytes) plus the bits that the most still-uncovered terms need; a term is applied by the first
@@ -1402,41 +1378,6 @@ PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
     return plan;
 }
 
-// tables and wide terms go to the device in one upload; the launches get their device pointers
-void Engine::upload_pauli_plan(PauliPlan& plan) {
-    const size_t table_bytes = plan.tables.size() * sizeof(double2), wide_bytes = plan.wide.size() * sizeof(k::PauliTerm);
-    if (table_bytes + wide_bytes == 0) return;
-    std::vector<char> blob(table_bytes + wide_bytes);
-    if (table_bytes) std::memcpy(blob.data(), plan.tables.data(), table_bytes);
-    if (wide_bytes) std::memcpy(blob.data() + table_bytes, plan.wide.data(), wide_bytes);
-    const char* d = static_cast<const char*>(small_upload(blob.data(), blob.size()));
-    for (size_t i = 0; i < plan.launches.size(); ++i)
-        plan.launches[i].w_in = plan.table_at[i] >= 0 ? reinterpret_cast<const double2*>(d) + plan.table_at[i] : nullptr;
-    plan.d_wide = wide_bytes ? reinterpret_cast<const k::PauliTerm*>(d + table_bytes) : nullptr;
-}
-
-// u <- scale * sum_t c_t P_t in   (and optionally acc += u on the control subspace with |u|^2 summed into d_norm)
-void Engine::run_pauli_plan(PauliPlan& plan, const double2* in, double2* u, double sre, double sim, double2* acc, uint64_t cmask,
-                            double* d_norm) {
-    bool first = true;
-    if (!plan.wide.empty()) {
-        k::pauli_gather_accumulate(ctx(), in, u, local_amps(), plan.d_wide, int(plan.wide.size()), true);
-        first = false;
-    }
-    for (size_t i = 0; i < plan.launches.size(); ++i) {
-        k::PauliTileArgs& a = plan.launches[i];
-        a.first = first ? 1 : 0;
-        a.final = i + 1 == plan.launches.size() ? 1 : 0;
-        a.expectation = 0;
-        a.sre = sre;
-        a.sim = sim;
-        a.cmask = cmask;
-        const int grid = k::pauli_tile_pass(ctx(), in, u, a.final ? acc : nullptr, a, d_partials_);
-        if (a.final && acc != nullptr && d_norm != nullptr) k::reduce_partials(ctx(), d_partials_, grid, d_norm, false);
-        first = false;
-    }
-}
-
 double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, size_t n_ids) {
     run();
     auto all_terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);  // logical masks
@@ -1459,21 +1400,33 @@ double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, si
             done[i] = 1;
             --left;
         }
-        if (batch.empty()) throw RuntimeErr("get_expectation_value(): a term flips more qubits than one shard holds");
+        if (batch.empty()) {
+            // what is left flips more qubits than one shard holds: no remap brings those partners on-device.  Apply the
+            // rest of the operator with the partner amplitudes read from the peers' shards, then <psi|u>.
+            std::vector<k::PauliTerm> rest;
+            for (size_t i = 0; i < all_terms.size(); ++i)
+                if (!done[i]) rest.push_back(all_terms[i]);
+            PauliProgram prog = build_pauli_program(rest);
+            ensure_scratch(*scratch1_, local_amps() * sizeof(double2));
+            const std::vector<const double2*> src = pauli_sources(prog, *state_);
+            dist_->barrier_on_stream();  // every rank's state is final before anybody reads it
+            run_pauli_program(prog, src, scratch1_->amps(), 1.0, 0.0, nullptr, 0, nullptr);
+            dist_->barrier_on_stream();  // the state may change again only after every peer has read it
+            k::dot_real(ctx(), psi(), scratch1_->amps(), local_amps(), d_partials_, d_acc, true);
+            break;
+        }
         if (dist_) {
             std::vector<uint32_t> need;
             for (int p = 0; p < n_; ++p)
                 if ((need_mask >> p) & 1) need.push_back(uint32_t(p));
             make_local(need);
         }
-        to_physical(batch, loc_, n_, rank_);
-        std::stable_sort(batch.begin(), batch.end(),
-                         [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
         const bool active = !dist_ || (uint64_t(rank_) & dist_->free_rank_bits_mask()) == 0;
         if (!active) continue;
         // tile-able terms: one read of the state per tile-bit set; the rest: one pair sweep per distinct xmask
-        PauliPlan plan = plan_pauli_tiles(batch, L_);
-        upload_pauli_plan(plan);
+        PauliProgram prog = build_pauli_program(batch);  // the batch's X/Y support is on-device: one group, this rank's shard
+        if (prog.reads_peers()) throw RuntimeErr("internal: X on a rank bit was not remapped");
+        PauliPlan& plan = prog.groups[0].plan;
         for (auto& a : plan.launches) {
             if (a.n_terms == 0 && a.n_outside == 0 && a.w_in == nullptr) continue;
             a.expectation = 1;
@@ -1491,32 +1444,142 @@ double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, si
     return allreduce_sum(read_scalar(d_acc));
 }
 
-// X-support of a term list as logical positions; in a sharded run it has to fit on the local bits all at once because
-// the out-of-place vectors of apply_qubit_operator / emulate_time_evolution are not re-laid-out between terms.
-static std::vector<uint32_t> x_support(const std::vector<k::PauliTerm>& terms, int n, int local_bits, const char* who) {
+// X/Y support of a term list as logical positions
+static std::vector<uint32_t> x_support(const std::vector<k::PauliTerm>& terms, int n) {
     uint64_t m = 0;
     for (auto& tm : terms) m |= tm.xmask;
     std::vector<uint32_t> need;
     for (int p = 0; p < n; ++p)
         if ((m >> p) & 1) need.push_back(uint32_t(p));
-    if (int(need.size()) > local_bits)
-        throw RuntimeErr(std::string(who) + ": in a sharded run the X/Y terms of the operator may touch at most as many "
-                         "qubits as one shard holds (" + std::to_string(local_bits) + ")");
     return need;
+}
+
+Engine::PauliProgram Engine::build_pauli_program(const std::vector<k::PauliTerm>& logical) {
+    std::map<int, std::vector<k::PauliTerm>> by_rank;
+    by_rank[0];  // the own-shard group always exists (it finalises even when it has no term)
+    for (auto t : logical) {
+        uint64_t x = 0, z = 0;
+        int xr = 0, zr = 0;
+        for (int p = 0; p < n_; ++p) {
+            const uint64_t bit = uint64_t(1) << p;
+            if (loc_[p] < 64) {
+                if (t.xmask & bit) x |= uint64_t(1) << loc_[p];
+                if (t.zmask & bit) z |= uint64_t(1) << loc_[p];
+            } else {
+                if (t.xmask & bit) xr |= 1 << (loc_[p] - 64);
+                if (t.zmask & bit) zr |= 1 << (loc_[p] - 64);
+            }
+        }
+        // the sign (-1)^{popcount(s & zmask)} is taken on the SOURCE index s = j ^ xmask: its rank bits are rank ^ xr
+        if (__builtin_popcount(unsigned((rank_ ^ xr) & zr)) & 1) {
+            t.cre = -t.cre;
+            t.cim = -t.cim;
+        }
+        t.xmask = x;
+        t.zmask = z;
+        by_rank[xr].push_back(t);
+    }
+    PauliProgram prog;
+    // peer groups first, the own-shard group last: its last launch scales / accumulates
+    for (auto it = by_rank.rbegin(); it != by_rank.rend(); ++it) {
+        PauliProgram::Group g;
+        g.xr = it->first;
+        std::stable_sort(it->second.begin(), it->second.end(),
+                         [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+        g.plan = plan_pauli_tiles(it->second, L_);
+        prog.groups.push_back(std::move(g));
+    }
+    // tables and wide terms of every group go to the device in one upload
+    std::vector<char> blob;
+    std::vector<size_t> table_off, wide_off;
+    for (auto& g : prog.groups) {
+        table_off.push_back(blob.size());
+        const char* tb = reinterpret_cast<const char*>(g.plan.tables.data());
+        blob.insert(blob.end(), tb, tb + g.plan.tables.size() * sizeof(double2));
+    }
+    for (auto& g : prog.groups) {
+        wide_off.push_back(blob.size());
+        const char* wb = reinterpret_cast<const char*>(g.plan.wide.data());
+        blob.insert(blob.end(), wb, wb + g.plan.wide.size() * sizeof(k::PauliTerm));
+    }
+    if (!blob.empty()) {
+        const char* d = static_cast<const char*>(small_upload(blob.data(), blob.size()));
+        for (size_t gi = 0; gi < prog.groups.size(); ++gi) {
+            PauliPlan& plan = prog.groups[gi].plan;
+            for (size_t i = 0; i < plan.launches.size(); ++i)
+                plan.launches[i].w_in =
+                    plan.table_at[i] >= 0 ? reinterpret_cast<const double2*>(d + table_off[gi]) + plan.table_at[i] : nullptr;
+            plan.d_wide = plan.wide.empty() ? nullptr : reinterpret_cast<const k::PauliTerm*>(d + wide_off[gi]);
+        }
+    }
+    return prog;
+}
+
+// where every group of the program reads from when the operator is applied to `buf` (this rank's vector of that role)
+std::vector<const double2*> Engine::pauli_sources(const PauliProgram& prog, const GrowBuffer& buf) {
+    std::vector<const double2*> src;
+    for (auto& g : prog.groups) {
+        if (g.xr == 0) {
+            src.push_back(buf.amps());
+            continue;
+        }
+        const double2* p = nullptr;
+        try {
+            p = dist_ ? dist_->peer_buffer(rank_ ^ g.xr, buf) : nullptr;
+        } catch (const std::runtime_error& e) {
+            throw CudaErr(e.what());
+        }
+        if (!p)
+            throw RuntimeErr("the operator flips more qubits than one shard holds, which needs peer-mapped shards "
+                             "(not available here: PQB_REMAP_P2P=0 or no peer access between the GPUs)");
+        src.push_back(p);
+    }
+    return src;
+}
+
+// u <- scale * sum_t c_t P_t in   (and optionally acc += u on the control subspace with |u|^2 summed into d_norm)
+void Engine::run_pauli_program(PauliProgram& prog, const std::vector<const double2*>& src, double2* u, double sre, double sim,
+                               double2* acc, uint64_t cmask, double* d_norm) {
+    bool first = true;
+    for (size_t gi = 0; gi < prog.groups.size(); ++gi) {
+        PauliPlan& plan = prog.groups[gi].plan;
+        const bool last_group = gi + 1 == prog.groups.size();
+        if (!plan.wide.empty()) {
+            k::pauli_gather_accumulate(ctx(), src[gi], u, local_amps(), plan.d_wide, int(plan.wide.size()), first);
+            first = false;
+        }
+        for (size_t i = 0; i < plan.launches.size(); ++i) {
+            k::PauliTileArgs& a = plan.launches[i];
+            if (!last_group && a.n_terms == 0 && a.n_outside == 0 && a.w_in == nullptr) continue;  // nothing to add
+            a.first = first ? 1 : 0;
+            a.final = last_group && i + 1 == plan.launches.size() ? 1 : 0;
+            a.expectation = 0;
+            a.sre = sre;
+            a.sim = sim;
+            a.cmask = cmask;
+            const int grid = k::pauli_tile_pass(ctx(), src[gi], u, a.final ? acc : nullptr, a, d_partials_);
+            if (a.final && acc != nullptr && d_norm != nullptr) k::reduce_partials(ctx(), d_partials_, grid, d_norm, false);
+            first = false;
+        }
+    }
 }
 
 void Engine::apply_qubit_operator(const TermsView& t, const uint32_t* ids, size_t n_ids) {
     run();
     auto terms = build_terms(t, ids, n_ids, false, nullptr, nullptr);
-    if (dist_) make_local(x_support(terms, n_, L_, "apply_qubit_operator()"));
-    to_physical(terms, loc_, n_, rank_);
-    std::stable_sort(terms.begin(), terms.end(),
-                     [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+    if (dist_) {
+        // bring the X/Y support on-device when it fits; otherwise the partner amplitudes are read from the peers' shards
+        const std::vector<uint32_t> need = x_support(terms, n_);
+        if (int(need.size()) <= L_) make_local(need);
+    }
+    PauliProgram prog = build_pauli_program(terms);
     const size_t bytes = local_amps() * sizeof(double2);
     ensure_scratch(*scratch1_, bytes);
-    PauliPlan plan = plan_pauli_tiles(terms, L_);
-    upload_pauli_plan(plan);
-    run_pauli_plan(plan, psi(), scratch1_->amps(), 1.0, 0.0, nullptr, 0, nullptr);
+    const std::vector<const double2*> src = pauli_sources(prog, *state_);
+    const bool peers = prog.reads_peers();
+    if (peers) dist_->barrier_on_stream();  // every rank's state is final before anybody reads it
+    run_pauli_program(prog, src, scratch1_->amps(), 1.0, 0.0, nullptr, 0, nullptr);
+    if (peers) dist_->barrier_on_stream();  // nobody reuses its old state buffer while a peer still reads it
     std::swap(state_, scratch1_);
 }
 
@@ -1532,10 +1595,11 @@ void Engine::emulate_time_evolution(const TermsView& t, double time, const uint3
     const std::complex<double> correction = std::exp(std::complex<double>(0.0, -time * tr / double(s)));
     std::vector<uint32_t> cl;
     for (size_t i = 0; i < nc; ++i) cl.push_back(pos_of(ctrl[i], "emulate_time_evolution(): Unknown control qubit id."));
-    if (dist_) make_local(x_support(terms, n_, L_, "emulate_time_evolution()"));
-    to_physical(terms, loc_, n_, rank_);
-    std::stable_sort(terms.begin(), terms.end(),
-                     [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
+    if (dist_) {
+        const std::vector<uint32_t> need = x_support(terms, n_);
+        if (int(need.size()) <= L_) make_local(need);
+    }
+    PauliProgram prog = build_pauli_program(terms);
     uint64_t cmask = 0;
     bool active = true;  // accumulation is masked by the controls; H itself acts everywhere (simulator.hpp:411-425)
     for (auto lp : cl) {
@@ -1547,26 +1611,32 @@ void Engine::emulate_time_evolution(const TermsView& t, double time, const uint3
     const size_t bytes = local_amps() * sizeof(double2);
     ensure_scratch(*scratch1_, bytes);
     ensure_scratch(*scratch2_, bytes);
-    PauliPlan plan = plan_pauli_tiles(terms, L_);
-    upload_pauli_plan(plan);
+    // the Taylor vectors alternate between the two scratch buffers; with peer groups both are read by the partners
+    const bool peers = prog.reads_peers();
+    std::vector<const double2*> src_v = pauli_sources(prog, *scratch1_), src_u = pauli_sources(prog, *scratch2_);
     double* d_norm = d_scalars_;
     for (unsigned i = 0; i < s; ++i) {
         double2* v = scratch1_->amps();
         double2* u = scratch2_->amps();
+        std::vector<const double2*>* sv = &src_v;
+        std::vector<const double2*>* su = &src_u;
         PQB_CHECK(cudaMemcpyAsync(v, psi(), bytes, cudaMemcpyDeviceToDevice, stream_));
+        if (peers) dist_->barrier_on_stream();  // every rank's v is in place before a partner reads it
         double nrm_change = 1.0;
         for (unsigned kk = 0; nrm_change > 1.e-12; ++kk) {
             // coeff = (-time * I) / (s * (k + 1))
             const double cim = -time / double(s * (kk + 1));
             if (active) {
-                run_pauli_plan(plan, v, u, 0.0, cim, psi(), cmask, d_norm);
+                run_pauli_program(prog, *sv, u, 0.0, cim, psi(), cmask, d_norm);
                 nrm_change = read_scalar(d_norm);
             } else {
-                run_pauli_plan(plan, v, u, 0.0, cim, nullptr, 0, nullptr);
+                run_pauli_program(prog, *sv, u, 0.0, cim, nullptr, 0, nullptr);
                 nrm_change = 0.0;
             }
+            // (the all-reduce is also the rendezvous that keeps a rank from overwriting a vector a partner still reads)
             nrm_change = std::sqrt(allreduce_sum(nrm_change));
             std::swap(v, u);
+            std::swap(sv, su);
         }
         if (active) k::scale_masked(ctx(), psi(), local_amps(), cmask, correction.real(), correction.imag());
     }

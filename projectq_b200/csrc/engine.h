@@ -165,9 +165,23 @@ private:
     void serial_exchange(const std::vector<std::pair<int, int>>& swaps);
     void pipelined_exchange(const std::vector<Launch>& tail, const std::vector<Launch>& head,
                             const std::vector<uint8_t>& slice_bits);
-    void upload_pauli_plan(PauliPlan& plan);
-    void run_pauli_plan(PauliPlan& plan, const double2* in, double2* u, double sre, double sim, double2* acc, uint64_t cmask,
-                        double* d_norm);
+    // An operator as the engine executes it: its terms grouped by the rank whose shard holds their partner amplitudes.
+    // (P psi)[j] needs psi[j ^ xmask]; the local part of xmask stays inside this rank's shard, an X/Y on a qubit that sits on a
+    // rank bit means the partner amplitude lives at the same local index on rank ^ xr.  Group 0 (xr = 0) reads this rank's own
+    // vector; the others read the partner's vector through peer-mapped memory (NVLink), so an operator that flips more qubits
+    // than one shard holds — a transverse field on every qubit of a sharded state — needs no remap at all.
+    struct PauliProgram {
+        struct Group {
+            int xr = 0;
+            PauliPlan plan;
+        };
+        std::vector<Group> groups;
+        bool reads_peers() const { return groups.size() > 1 || (!groups.empty() && groups[0].xr != 0); }
+    };
+    PauliProgram build_pauli_program(const std::vector<k::PauliTerm>& logical_terms);
+    std::vector<const double2*> pauli_sources(const PauliProgram& prog, const GrowBuffer& buf);
+    void run_pauli_program(PauliProgram& prog, const std::vector<const double2*>& src, double2* u, double sre, double sim,
+                           double2* acc, uint64_t cmask, double* d_norm);
     void check_exchange_error();
     bool leaves_from_low_bit(int local_bit, size_t n_swaps) const;
     // CUDA events: a pool, and (start, stop) pairs whose elapsed time is added to a counter once they have completed

@@ -519,6 +519,27 @@ void norm_masked(const Ctx& c, const double2* psi, uint64_t n_amps, uint64_t mas
     launched(c);
 }
 
+__global__ void __launch_bounds__(256) dot_real_kernel(const double2* __restrict__ a, const double2* __restrict__ b,
+                                                       uint64_t n_amps, double* __restrict__ partials) {
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_amps; i += step) {
+        const double2 x = a[i], y = b[i];
+        acc += x.x * y.x + x.y * y.y;
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+void dot_real(const Ctx& c, const double2* a, const double2* b, uint64_t n_amps, double* d_partials, double* d_out,
+              bool accumulate) {
+    const int grid = reduce_grid(n_amps, 256 * 8);
+    dot_real_kernel<<<grid, 256, 0, c.stream>>>(a, b, n_amps, d_partials);
+    launched(c);
+    final_sum_kernel<<<1, 256, 0, c.stream>>>(d_partials, grid, d_out, accumulate ? 1 : 0);
+    launched(c);
+}
+
 __global__ void __launch_bounds__(256) collapse_scale_kernel(double2* __restrict__ psi, uint64_t n_amps, uint64_t mask,
                                                              uint64_t val, double scale) {
     const uint64_t step = uint64_t(gridDim.x) * blockDim.x;

@@ -36,6 +36,9 @@ void apply_diagonal(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t
 void norm_masked(const Ctx& c, const double2* psi, uint64_t n_amps, uint64_t mask, uint64_t val, double* d_partials,
                  double* d_out);
 // psi_i <- (i & mask) == val ? psi_i * scale : 0   (reference: simulator.hpp:174-185, 478-484)
+// d_out (+)= sum_j Re(conj(a_j) b_j)
+void dot_real(const Ctx& c, const double2* a, const double2* b, uint64_t n_amps, double* d_partials, double* d_out,
+              bool accumulate);
 void collapse_scale(const Ctx& c, double2* psi, uint64_t n_amps, uint64_t mask, uint64_t val, double scale);
 // psi_i *= scale
 void scale_all(const Ctx& c, double2* psi, uint64_t n_amps, double scale);

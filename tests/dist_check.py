@@ -140,6 +140,31 @@ def main():
     gpu.apply_qubit_operator(cterms, ids)
     chk.apply_qubit_operator(cterms, ids)
     same(gpu, chk, "apply_qubit_operator", tol=1e-10)
+    # 3b. operators that flip MORE qubits than one shard holds (a transverse field on every qubit): no remap can bring the
+    #     whole X/Y support on-device, the partner amplitudes are read from the peers' shards over NVLink
+    nrm = float(np.linalg.norm(chk.cheat()[1]))
+    wfn = chk.cheat()[1] / nrm
+    back0 = {v: k for k, v in chk.cheat()[0].items()}
+    order0 = [back0[p] for p in range(n)]
+    gpu.set_wavefunction(wfn, order0)
+    chk.set_wavefunction(wfn, order0)
+    full = tfim_terms(n) + [([(q, "Y" if q % 3 == 0 else "X") for q in range(n)], 0.21), ([(0, "Y"), (n - 1, "Z"), (5, "X")], -0.4)]
+    if expect != "nccl":  # needs peer-mapped shards
+        gpu.emulate_time_evolution(full, 0.05, list(range(n)), [])
+        chk.emulate_time_evolution(full, 0.05, list(range(n)), [])
+        same(gpu, chk, "time evolution, X on every qubit")
+        cfull = [(t, c * (0.8 - 0.3j)) for t, c in full]
+        gpu.apply_qubit_operator(cfull, ids)
+        chk.apply_qubit_operator(cfull, ids)
+        same(gpu, chk, "apply_qubit_operator, X on every qubit", tol=1e-10)
+        e1, e2 = gpu.get_expectation_value(full, ids), chk.get_expectation_value(full, ids)
+        assert abs(e1 - e2) < 1e-10 * max(1.0, abs(e2)), (e1, e2)
+    else:
+        try:
+            gpu.get_expectation_value(full, ids)
+            raise AssertionError("a string on every qubit needs peer-mapped shards: expected RuntimeError without them")
+        except RuntimeError:
+            pass
     nrm = float(np.linalg.norm(chk.cheat()[1]))
     wf = chk.cheat()[1] / nrm
     order = [int(x) for x in rng.permutation(n)]
