@@ -1320,21 +1320,33 @@ PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
                 generic.push_back(i);
             }
         }
+        // order the terms by where the kernel finds the partner amplitude: in the thread's registers (the x bits are all
+        // among the top tile-coordinate bits, which number a thread's own elements) or in the shared tile
+        constexpr uint32_t kThreadBits = 8;  // pauli_tile_kernel: 256 threads, element e of thread t = tile coordinate e * 256 + t
+        auto klass = [&](int i) {
+            const uint32_t xl = uint32_t(extract_bits(terms[i].xmask, base.tile_pos, T));
+            return xl != 0 && T == k::kTileBits && (xl & ((1u << kThreadBits) - 1)) == 0 ? 0 : 1;
+        };
+        std::stable_sort(generic.begin(), generic.end(), [&](int x, int y) { return klass(x) < klass(y); });
         size_t at_g = 0, at_o = 0;
         bool first_chunk = true;
         do {
             k::PauliTileArgs a = base;
-            a.all_real = 1;
             for (; at_g < generic.size() && a.n_terms < k::kTileTerms; ++at_g) {
                 const k::PauliTerm& tm = terms[generic[at_g]];
                 plan.launch_of_term[generic[at_g]] = int(plan.launches.size());
-                a.coef[a.n_terms] = make_double2(tm.cre, tm.cim);
-                a.xl[a.n_terms] = uint32_t(extract_bits(tm.xmask, base.tile_pos, T));
-                a.zl[a.n_terms] = uint32_t(extract_bits(tm.zmask, base.tile_pos, T));
+                const uint32_t xl = uint32_t(extract_bits(tm.xmask, base.tile_pos, T));
+                const uint32_t zl = uint32_t(extract_bits(tm.zmask, base.tile_pos, T));
+                // sign on the source coordinate t ^ xl: parity((t ^ xl) & zl) = parity(t & zl) ^ parity(xl & zl)
+                const double sgn = (__builtin_popcount(xl & zl) & 1) ? -1.0 : 1.0;
+                a.coef[a.n_terms] = make_double2(sgn * tm.cre, sgn * tm.cim);
+                a.xl[a.n_terms] = xl;
+                a.zl[a.n_terms] = zl;
                 a.z_out[a.n_terms] = tm.zmask & ~S;
-                if (a.zl[a.n_terms] != 0) a.any_zl = 1;
-                if (tm.cim != 0.0) a.all_real = 0;
+                a.general[a.n_terms] = (zl != 0 || tm.cim != 0.0) ? 1 : 0;
+                const int c = klass(generic[at_g]);
                 ++a.n_terms;
+                if (c == 0) a.n_reg = a.n_terms;
             }
             for (; at_o < outside.size() && a.n_outside < k::kTileTerms; ++at_o) {
                 const k::PauliTerm& tm = terms[outside[at_o]];

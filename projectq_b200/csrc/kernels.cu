@@ -253,8 +253,14 @@ __global__ void __launch_bounds__(THREADS, MINB) apply_dense_lowbits_kernel(doub
 // TMA unit (cp.async.bulk shared -> global).  The load/store pipe carries 32 shared-memory operations per thread and no
 // LDG/STG; three CTAs (3 x 68 KB of shared memory) are resident per SM so that one CTA's transfers overlap another's math.
 constexpr int kTmaRowBytes = 272;
+#define Q_LOG2(q) ((q) == 1 ? 0 : (q) == 2 ? 1 : (q) == 4 ? 2 : 3)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
 
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) apply_dense_k4_low_tma_kernel(double2* __restrict__ psi,
@@ -301,6 +307,248 @@ __global__ void __launch_bounds__(THREADS, MINB) apply_dense_k4_low_tma_kernel(d
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(run), "r"(row_s), "r"(256) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the row must stay intact until the TMA unit has read it
+}
+
+// MODE 4 (separate kernel): k = 4 on the FP64 tensor pipe.  Measured on this B200 (tools/fp64_power.cu,
+// profiles/r2_fp64_power_*): DMMA.884 sustains 37.1 TFLOP/s at ~235 W above idle, DFMA 32.7 TFLOP/s at ~410 W — the tensor
+// path spends about half the energy per flop, and the k = 4 pass is the kernel that runs into the 1 kW cap (FP64 pipe 88 %
+// busy at the capped clock).  The complex 16x16 mat-vec is the real product [Re; Im](out) = [[A, -B], [B, A]] [Re; Im](in),
+// 32x32 real, done for 8 amplitude groups at a time as 4 row blocks x 8 k-steps of mma.m8n8k4.f64:
+//   * B operand (4 x 8, lane holds row lane%4 of column lane/4): column n = group 8q + n, so the groups of a batch are 8
+//     neighbouring amplitudes (needs the three lowest index bits free); lane (kc, n) loads members kc, kc+4, kc+8, kc+12 of
+//     group n — four 128-bit loads, 128-byte runs per request — and k-step 2i / 2i+1 takes the real / imaginary part of
+//     member kc + 4i;
+//   * A operand (8 x 4, lane holds row lane/4, column lane%4): matrix entries U[m + 8h][kc + 4i], 8 complex numbers per
+//     lane kept in registers as Re, Im and -Im;
+//   * D (8 x 8, lane holds row lane/4, columns 2(lane%4), +1): row block 2h is Re, 2h+1 is Im of members m + 8h, so a lane
+//     ends up with member m (+8) of two NEIGHBOURING groups: one 256-bit store each.
+// 4 x 8 x 32 DMMA-lanes replace 2048 DFMA per group; the issue slots per amplitude drop 8x.
+// Staging: a warp takes Q neighbouring batches per step, so every member's amplitudes form one run of Q * 128 bytes.  The
+// runs are copied global -> shared with cp.async by lanes in ADDRESS order (lane l moves the l-th 16 bytes of a run: the
+// copy unit merges sectors only between neighbouring lanes — with the fragment order, lane = 4 n + kc, it fetched every
+// 32-byte sector twice), STAGES steps ahead, so the loads in flight cost no registers; after cp.async.wait_group + __syncwarp
+// each lane picks its B fragments out of the rows (row pitch = run + 32 bytes: conflict-free for the fragment order).
+// Warps are persistent and walk the steps with a grid stride.
+template <int Q, int STAGES, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) apply_dense_k4_dmma_kernel(double2* __restrict__ psi,
+                                                                      const __grid_constant__ DenseArgs<4> p) {
+    constexpr int QL = Q_LOG2(Q), RUN = 8 * Q;           // amplitudes per run
+    constexpr int ROWS_PER_COPY = 32 / RUN;               // members one cp.async instruction covers (4 / Q)
+    constexpr uint32_t PITCH = RUN * 16 + 32, STAGE_BYTES = 16 * PITCH;
+    extern __shared__ __align__(16) unsigned char dmma_ring[];  // [warp][stage][16 members][PITCH]
+    const int lane = threadIdx.x & 31, kc = lane & 3, hi = lane >> 2;  // hi = column n of B = row m of A and D
+    // matrix fragments
+    double are[2][4], aim[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 u = p.m[(hi + 8 * h) * 16 + kc + 4 * i];
+            are[h][i] = u.x;
+            aim[h][i] = u.y;
+            // pin the fragments in registers: left alone, the compiler re-reads them from the parameter bank inside the loop,
+            // and a constant load whose address differs per lane is replayed lane by lane (ncu: mio_throttle 29)
+            asm volatile("" : "+d"(are[h][i]), "+d"(aim[h][i]));
+        }
+    uint64_t stride[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) stride[l] = uint64_t(1) << p.tpos[l];
+    auto offset = [&](int j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+            if ((j >> l) & 1) off += stride[l];
+        return off;
+    };
+    // copy side: lane -> (member within the instruction, position in the run)
+    const int copy_row = lane / RUN, copy_col = lane % RUN;
+    const uint64_t copy_off = offset(copy_row) + copy_col;
+    // fragment side: member kc + 4 i of group n = hi
+    const uint32_t frag_off = uint32_t(kc) * PITCH + uint32_t(hi) * 16;
+    const uint64_t off_m = offset(hi) + 2 * kc;
+    const uint64_t n_steps = p.n_items >> 3 >> QL;
+    const uint64_t n_warps = (uint64_t(gridDim.x) * THREADS) >> 5;
+    const uint64_t w0 = (uint64_t(blockIdx.x) * THREADS + threadIdx.x) >> 5;
+    const uint32_t ring = smem_addr(dmma_ring) + (threadIdx.x >> 5) * (STAGES * STAGE_BYTES);
+    __shared__ uint64_t step_base[THREADS / 32][STAGES];  // index of a step's first amplitude: spread once, used twice
+    uint64_t* my_base = step_base[threadIdx.x >> 5];
+    auto issue = [&](uint64_t step, int stage) {
+        if (step < n_steps) {
+            const uint64_t b = insert_zero_bits(step << (3 + QL), p.ins_pos, p.n_ins) | p.ctrl_mask;
+            if (lane == 0) my_base[stage] = b;
+            const double2* src = psi + b + copy_off;
+            const uint32_t dst = ring + stage * STAGE_BYTES + uint32_t(copy_row) * PITCH + uint32_t(copy_col) * 16;
+#pragma unroll
+            for (int u = 0; u < 16 / ROWS_PER_COPY; ++u)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * ROWS_PER_COPY * PITCH),
+                             "l"(src + offset(u * ROWS_PER_COPY))
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(w0 + s * n_warps, s);
+    int stage = 0;
+    for (uint64_t step = w0; step < n_steps; step += n_warps) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        __syncwarp();  // every lane's copies of this step have landed; my_base[stage]; the stage refilled below is drained
+        issue(step + (STAGES - 1) * n_warps, stage == 0 ? STAGES - 1 : stage - 1);
+        double2* dst0 = psi + my_base[stage] + off_m;
+        const uint32_t rows = ring + stage * STAGE_BYTES + frag_off;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            double2 in[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) in[i] = lds_d2(rows + (4 * i) * PITCH + j * 128);
+            double d[4][2];
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) d[rb][0] = d[rb][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const double b = part == 0 ? in[i].x : in[i].y;
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb) {
+                        const int h = rb >> 1, po = rb & 1;
+                        const double a = po == part ? are[h][i] : (po == 0 ? -aim[h][i] : aim[h][i]);  // (the negation is an operand modifier)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(d[rb][0]), "+d"(d[rb][1])
+                                     : "d"(a), "d"(b));
+                    }
+                }
+            }
+            double2* dst = dst0 + 8 * j;
+            st256(dst, make_double2(d[0][0], d[1][0]), make_double2(d[0][1], d[1][1]));
+            st256(dst + stride[3], make_double2(d[2][0], d[3][0]), make_double2(d[2][1], d[3][1]));
+        }
+        __syncwarp();  // all lanes are done reading this stage before a later iteration refills it
+        stage = stage == STAGES - 1 ? 0 : stage + 1;
+    }
+}
+
+// Register form of the same kernel: a lane loads its B fragments straight from global memory (ld.global.v2.f64: the LSU
+// coalesces the four 128-byte runs of a request whatever the lane order), a step of 4 batches = 16 loads per lane in flight,
+// and the warps of the persistent CTAs overlap one another's load, DMMA and store phases.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) apply_dense_k4_dmma_reg_kernel(double2* __restrict__ psi,
+                                                                          const __grid_constant__ DenseArgs<4> p) {
+    constexpr int Q = 4;
+    const int lane = threadIdx.x & 31, kc = lane & 3, hi = lane >> 2;
+    double are[2][4], aim[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 u = p.m[(hi + 8 * h) * 16 + kc + 4 * i];
+            are[h][i] = u.x;
+            aim[h][i] = u.y;
+            asm volatile("" : "+d"(are[h][i]), "+d"(aim[h][i]));
+        }
+    uint64_t stride[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) stride[l] = uint64_t(1) << p.tpos[l];
+    auto offset = [&](int j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+            if ((j >> l) & 1) off += stride[l];
+        return off;
+    };
+    const uint64_t off_in = offset(kc) + hi, off_m = offset(hi) + 2 * kc;
+    const uint64_t n_steps = p.n_items >> 5;
+    const uint64_t n_warps = (uint64_t(gridDim.x) * THREADS) >> 5;
+    for (uint64_t step = (uint64_t(blockIdx.x) * THREADS + threadIdx.x) >> 5; step < n_steps; step += n_warps) {
+        const uint64_t b = insert_zero_bits(step << 5, p.ins_pos, p.n_ins) | p.ctrl_mask;
+        const double2* src = psi + b + off_in;
+        double2 in[Q][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) in[j][i] = src[offset(4 * i) + 8 * j];
+        double2* dst0 = psi + b + off_m;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            double d[4][2];
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) d[rb][0] = d[rb][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const double bv = part == 0 ? in[j][i].x : in[j][i].y;
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb) {
+                        const int h = rb >> 1, po = rb & 1;
+                        const double a = po == part ? are[h][i] : (po == 0 ? -aim[h][i] : aim[h][i]);
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(d[rb][0]), "+d"(d[rb][1])
+                                     : "d"(a), "d"(bv));
+                    }
+                }
+            }
+            double2* dst = dst0 + 8 * j;
+            st256(dst, make_double2(d[0][0], d[1][0]), make_double2(d[0][1], d[1][1]));
+            st256(dst + stride[3], make_double2(d[2][0], d[3][0]), make_double2(d[2][1], d[3][1]));
+        }
+    }
+}
+
+template <int THREADS, int MINB>
+static void launch_dense_k4_dmma_reg(const Ctx& c, double2* psi, const DenseArgs<4>& args) {
+    const uint64_t warps = args.n_items >> 5;
+    uint64_t blocks = (warps * 32 + THREADS - 1) / THREADS;
+    if (blocks > uint64_t(148 * MINB)) blocks = 148 * MINB;
+    apply_dense_k4_dmma_reg_kernel<THREADS, MINB><<<unsigned(blocks), THREADS, 0, c.stream>>>(psi, args);
+    launched(c);
+}
+
+// PQB_DENSE_DMMA: 0 (default) = off, 1 = register form, 2 = cp.async ring form.  Off by default because it measures SLOWER
+// than the DFMA kernel in the sustained benchmark even though it leaves power on the table: 6.00-6.05 ms per pass at
+// 1.60-1.62 GHz against 5.83 ms at 1.41 GHz on the same box (profiles/r2_dmma_experiment.md) — both forms stop at a memory
+// path of ~5.75 ms (cp.async staging, or 12 resident warps of 152 registers whose load phases leave the DMMA pipe idle),
+// where the per-thread kernel with 24 resident warps streams the same bytes in 4.98 ms.
+static int dense_dmma_variant() {
+    static const int u = [] {
+        const char* e = getenv("PQB_DENSE_DMMA");
+        return e ? atoi(e) : 0;
+    }();
+    return u;
+}
+
+template <int Q, int STAGES, int THREADS, int MINB>
+static void launch_dense_k4_dmma_v(const Ctx& c, double2* psi, const DenseArgs<4>& args) {
+    constexpr size_t smem = size_t(THREADS / 32) * STAGES * 16 * (8 * Q * 16 + 32);
+    static bool configured = false;
+    if (!configured) {
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(apply_dense_k4_dmma_kernel<Q, STAGES, THREADS, MINB>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = true;
+    }
+    const uint64_t warps = args.n_items >> 3 >> Q_LOG2(Q);
+    uint64_t blocks = (warps * 32 + THREADS - 1) / THREADS;
+    if (blocks > uint64_t(148 * MINB)) blocks = 148 * MINB;  // persistent: the resident CTAs walk the steps
+    apply_dense_k4_dmma_kernel<Q, STAGES, THREADS, MINB><<<unsigned(blocks), THREADS, smem, c.stream>>>(psi, args);
+    launched(c);
+}
+
+// applies when the three lowest index bits are neither targets nor controls / slice bits
+static bool launch_dense_k4_dmma(const Ctx& c, double2* psi, int n_bits, const DenseArgs<4>& args) {
+    const int v = dense_dmma_variant();
+    if (v == 0 || args.ins_pos[0] < 3) return false;
+    // the Q batches of a step are neighbours in memory when the bits below 3 + log2 Q are free as well
+    int free_low = 0;
+    while (free_low < n_bits && (args.n_ins == 0 || free_low < args.ins_pos[0])) ++free_low;
+    if (args.n_ins > 0 && free_low > args.ins_pos[0]) free_low = args.ins_pos[0];
+    if (free_low >= 5) {
+        if (v == 2)
+            launch_dense_k4_dmma_v<4, 3, 256, 1>(c, psi, args);
+        else
+            launch_dense_k4_dmma_reg<128, 3>(c, psi, args);
+        return true;
+    }
+    launch_dense_k4_dmma_v<1, 4, 256, 2>(c, psi, args);
+    return true;
 }
 
 static bool dense_tma_enabled() {
@@ -423,6 +671,9 @@ static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* 
         launch_dense_mode<K, 1, 1, (K >= 5 ? 128 : 256), (K == 3 ? 2 : (K <= 2 ? 4 : 3))>(c, psi, args);
     } else {
         fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host, slice);
+        if constexpr (K == 4) {
+            if (launch_dense_k4_dmma(c, psi, n_bits, args)) return;
+        }
         launch_dense_mode<K, 0, U0, T0, (K == 3 ? 2 : (K <= 2 ? 3 : 3))>(c, psi, args);
     }
 }
@@ -1203,17 +1454,12 @@ void pauli_apply(const Ctx& c, const double2* in, double2* out, uint64_t n_amps,
 // loop is one XOR, one 128-bit shared load and 2-4 DFMA per amplitude.
 constexpr int kTileElems = 8;  // 2^kTileBits / 256 threads
 
-__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
 
 // FULL: the tile has exactly kTileElems * THREADS amplitudes (every state of kTileBits or more local bits), so the element
 // loops carry no guards; the other instantiation serves tiny states.  Shared memory is addressed through 32-bit shared
 // addresses (ld.shared): with generic pointers the compiler re-derived the shared window for every load.
-template <int THREADS, bool FULL>
-__global__ void __launch_bounds__(THREADS, 3) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
+template <int THREADS, bool FULL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
                                                                 double2* __restrict__ acc,
                                                                 const __grid_constant__ PauliTileArgs a,
                                                                 double* __restrict__ partials) {
@@ -1221,6 +1467,9 @@ __global__ void __launch_bounds__(THREADS, 3) pauli_tile_kernel(const double2* _
     __shared__ double2 coef_s[kTileTerms];  // coefficients with this tile's outside-z sign applied
     __shared__ double2 w_out_s;             // sum of the outside-only diagonal terms for this tile
     __shared__ uint64_t goff_s[kTileElems]; // index bits contributed by the element number e (the same for every thread)
+    __shared__ uint64_t base_s[3];          // index bits of the current tile, the next one and the one after: spreading a tile
+                                            // number over the non-tile bits costs a few hundred instructions, so ONE thread
+                                            // does it, two tiles ahead, instead of every warp
     const uint32_t tile_amps = 1u << a.T;
     constexpr int LOG_THREADS = THREADS == 256 ? 8 : 7;
     const int n_e = FULL ? kTileElems : (tile_amps > uint32_t(THREADS) ? int(tile_amps / THREADS) : 1);
@@ -1232,10 +1481,14 @@ __global__ void __launch_bounds__(THREADS, 3) pauli_tile_kernel(const double2* _
     const uint64_t g_tid = coord_to_index(threadIdx.x & (tile_amps - 1));
     const bool mine = FULL || threadIdx.x < tile_amps;  // tiles smaller than the CTA (tiny states): the other threads idle
     const uint32_t buffers_s = smem_addr(tile_buffers), t16 = threadIdx.x * 16;
-    __syncthreads();                            // goff_s
+    if (threadIdx.x == 32 % THREADS) {
+        base_s[0] = insert_zero_bits(blockIdx.x, a.tile_pos, a.T);
+        base_s[1] = insert_zero_bits(uint64_t(blockIdx.x) + gridDim.x, a.tile_pos, a.T);
+    }
+    __syncthreads();                            // goff_s, base_s
     // asynchronous copy of one tile into one of the two buffers (16 bytes per thread and element, L2 -> shared directly)
-    auto fetch = [&](uint64_t tile_id, int buf) {
-        const uint64_t g0f = insert_zero_bits(tile_id, a.tile_pos, a.T) | g_tid;
+    auto fetch = [&](uint64_t tile_base, int buf) {
+        const uint64_t g0f = tile_base | g_tid;
         double2* dst = tile_buffers + size_t(buf) * tile_amps;
 #pragma unroll
         for (int e = 0; e < kTileElems; ++e)
@@ -1247,13 +1500,14 @@ __global__ void __launch_bounds__(THREADS, 3) pauli_tile_kernel(const double2* _
     };
     double red = 0.0;
     int buf = 0;
-    if (uint64_t(blockIdx.x) < a.n_tiles) fetch(blockIdx.x, 0);
-    for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x, buf ^= 1) {
-        const uint64_t base = insert_zero_bits(tid_tile, a.tile_pos, a.T);
+    int slot = 0;  // base_s[slot] belongs to the current tile
+    if (uint64_t(blockIdx.x) < a.n_tiles) fetch(base_s[0], 0);
+    for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x, buf ^= 1, slot = slot == 2 ? 0 : slot + 1) {
+        const uint64_t base = base_s[slot];
         const uint32_t tile_s = buffers_s + uint32_t(buf) * (tile_amps * 16);  // shared address of this tile
         auto at = [&](int e, uint32_t x16) { return lds_d2(tile_s + ((uint32_t(e) * (THREADS * 16) + t16) ^ x16)); };
         const bool more = tid_tile + gridDim.x < a.n_tiles;
-        if (more) fetch(tid_tile + gridDim.x, buf ^ 1);  // the other buffer was released by the barrier that ended the last tile
+        if (more) fetch(base_s[slot == 2 ? 0 : slot + 1], buf ^ 1);  // the other buffer was released by the barrier that ended the last tile
         if (int(threadIdx.x) < a.n_terms) {
             double2 c = a.coef[threadIdx.x];
             if (__popcll(base & a.z_out[threadIdx.x]) & 1) c = make_double2(-c.x, -c.y);
@@ -1273,100 +1527,138 @@ __global__ void __launch_bounds__(THREADS, 3) pauli_tile_kernel(const double2* _
         else
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        if (threadIdx.x == 32 % THREADS)  // (this slot was last read before the barrier that ended the previous tile)
+            base_s[slot == 0 ? 2 : slot - 1] = insert_zero_bits(tid_tile + 2 * uint64_t(gridDim.x), a.tile_pos, a.T);
         const uint64_t g0 = base | g_tid;
-        // diagonal part: (table of in-tile terms + per-tile scalar) * psi_j
-        double re[kTileElems], im[kTileElems];
+        double re[kTileElems] = {}, im[kTileElems] = {};
         const double2 w_out = w_out_s;
+        // s_j += c * v with the per-amplitude sign of a term that has z bits inside the tile
+        auto add_general = [&](int e, const double2 c, const double2 v, uint32_t par_tid, uint32_t zh) {
+            const bool neg = (par_tid ^ __popc(uint32_t(e) & zh)) & 1;  // parity of (tile coordinate & zl)
+            const double cx = neg ? -c.x : c.x, cy = neg ? -c.y : c.y;
+            re[e] = fma(cx, v.x, re[e]);
+            re[e] = fma(-cy, v.y, re[e]);
+            im[e] = fma(cx, v.y, im[e]);
+            im[e] = fma(cy, v.x, im[e]);
+        };
+        int k = 0;
+        {
+            // phase 1, the thread's own amplitudes in registers: the diagonal part, (table of in-tile terms + per-tile
+            // scalar) * psi_j, and the terms whose partner is another element of the same thread (xl = m * THREADS)
+            double2 self[kTileElems];
 #pragma unroll
-        for (int e = 0; e < kTileElems; ++e) {
-            re[e] = im[e] = 0.0;
-            if ((FULL || e < n_e) && mine) {
-                const uint32_t t = e * THREADS + threadIdx.x;
-                const double2 self = at(e, 0);
-                double wr = w_out.x, wi = w_out.y;
-                if (a.w_in != nullptr) {
-                    const double2 w = __ldg(a.w_in + t);
-                    wr += w.x;
-                    wi += w.y;
+            for (int e = 0; e < kTileElems; ++e) {
+                re[e] = im[e] = 0.0;
+                self[e] = make_double2(0.0, 0.0);
+                if ((FULL || e < n_e) && mine) {
+                    const uint32_t t = e * THREADS + threadIdx.x;
+                    self[e] = at(e, 0);
+                    double wr = w_out.x, wi = w_out.y;
+                    if (a.w_in != nullptr) {
+                        const double2 w = __ldg(a.w_in + t);
+                        wr += w.x;
+                        wi += w.y;
+                    }
+                    re[e] = wr * self[e].x - wi * self[e].y;
+                    im[e] = wr * self[e].y + wi * self[e].x;
                 }
-                re[e] = wr * self.x - wi * self.y;
-                im[e] = wr * self.y + wi * self.x;
+            }
+            if (FULL) {
+                for (; k < a.n_reg; ++k) {
+                    const double2 c = coef_s[k];
+                    const uint32_t m = a.xl[k] >> LOG_THREADS, zl = a.zl[k];
+                    const uint32_t par_tid = __popc(threadIdx.x & zl), zh = zl >> LOG_THREADS;
+                    const bool general = a.general[k];
+#pragma unroll
+                    for (int M = 1; M < kTileElems; ++M) {
+                        if (m != uint32_t(M)) continue;
+                        if (!general) {
+#pragma unroll
+                            for (int e = 0; e < kTileElems; ++e) {
+                                re[e] = fma(c.x, self[e ^ M].x, re[e]);
+                                im[e] = fma(c.x, self[e ^ M].y, im[e]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < kTileElems; ++e) add_general(e, c, self[e ^ M], par_tid, zh);
+                        }
+                    }
+                }
             }
         }
+        // phase 2, partners in the shared tile: one 128-bit shared load per amplitude and term (a diagonal term with z
+        // bits on both sides of the tile boundary is the case xl = 0).  All loads of a term are issued before its DFMAs.
         if (mine) {
-            if (a.any_zl) {
-                for (int k = 0; k < a.n_terms; ++k) {
-                    const uint32_t xl = a.xl[k], zl = a.zl[k];
-                    const double2 c = coef_s[k];
+            for (; k < a.n_terms; ++k) {
+                const uint32_t x16 = a.xl[k] << 4;
+                const double2 c = coef_s[k];
+                double2 v[kTileElems];
+                if (FULL && (x16 >> (LOG_THREADS + 4)) == 0) {  // the flip stays inside the thread number: immediate offsets
+                    const uint32_t addr = tile_s + (t16 ^ x16);
 #pragma unroll
-                    for (int e = 0; e < kTileElems; ++e) {
-                        if (FULL || e < n_e) {
-                            const uint32_t s = (e * THREADS + threadIdx.x) ^ xl;
-                            const double2 v = at(e, xl << 4);
-                            const bool neg = __popc(s & zl) & 1;
-                            const double cx = neg ? -c.x : c.x, cy = neg ? -c.y : c.y;
-                            re[e] = fma(cx, v.x, re[e]);
-                            re[e] = fma(-cy, v.y, re[e]);
-                            im[e] = fma(cx, v.y, im[e]);
-                            im[e] = fma(cy, v.x, im[e]);
-                        }
-                    }
+                    for (int e = 0; e < kTileElems; ++e) v[e] = lds_d2(addr + uint32_t(e) * (THREADS * 16));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kTileElems; ++e) v[e] = (FULL || e < n_e) ? at(e, x16) : make_double2(0.0, 0.0);
                 }
-            } else if (a.all_real) {  // real coefficients on pure X strings (a transverse field): 2 DFMA per amplitude and term
-                for (int k = 0; k < a.n_terms; ++k) {
-                    const uint32_t x16 = a.xl[k] << 4;
-                    const double cx = coef_s[k].x;
+                if (!a.general[k]) {  // real coefficient on a pure X string (a transverse field): 2 DFMA per amplitude
 #pragma unroll
                     for (int e = 0; e < kTileElems; ++e) {
-                        if (FULL || e < n_e) {
-                            const double2 v = at(e, x16);
-                            re[e] = fma(cx, v.x, re[e]);
-                            im[e] = fma(cx, v.y, im[e]);
-                        }
+                        re[e] = fma(c.x, v[e].x, re[e]);
+                        im[e] = fma(c.x, v[e].y, im[e]);
                     }
-                }
-            } else {
-                for (int k = 0; k < a.n_terms; ++k) {
-                    const uint32_t x16 = a.xl[k] << 4;
-                    const double2 c = coef_s[k];
+                } else {
+                    const uint32_t zl = a.zl[k];
+                    const uint32_t par_tid = __popc(threadIdx.x & zl), zh = zl >> LOG_THREADS;
 #pragma unroll
-                    for (int e = 0; e < kTileElems; ++e) {
-                        if (FULL || e < n_e) {
-                            const double2 v = at(e, x16);
-                            re[e] = fma(c.x, v.x, re[e]);
-                            re[e] = fma(-c.y, v.y, re[e]);
-                            im[e] = fma(c.x, v.y, im[e]);
-                            im[e] = fma(c.y, v.x, im[e]);
-                        }
-                    }
+                    for (int e = 0; e < kTileElems; ++e) add_general(e, c, v[e], par_tid, zh);
                 }
             }
         }
+        if (a.expectation) {
 #pragma unroll
-        for (int e = 0; e < kTileElems; ++e) {
-            if (!((FULL || e < n_e) && mine)) continue;
-            if (a.expectation) {
+            for (int e = 0; e < kTileElems; ++e) {
+                if (!((FULL || e < n_e) && mine)) continue;
                 const double2 self = at(e, 0);
                 red += self.x * re[e] + self.y * im[e];  // Re(conj(psi_j) s_j)
-                continue;
             }
-            const uint64_t g = g0 | goff_s[e];
-            double sr = re[e], si = im[e];
+        } else if (mine) {
+            // all loads of the partial sums (and of the accumulator) are in flight before the first store
             if (!a.first) {
-                const double2 prev = u[g];
-                sr += prev.x;
-                si += prev.y;
+                double2 prev[kTileElems];
+#pragma unroll
+                for (int e = 0; e < kTileElems; ++e)
+                    prev[e] = (FULL || e < n_e) ? __ldcg(u + (g0 | goff_s[e])) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int e = 0; e < kTileElems; ++e) {
+                    re[e] += prev[e].x;
+                    im[e] += prev[e].y;
+                }
             }
             if (!a.final) {
-                u[g] = make_double2(sr, si);
-                continue;
-            }
-            const double ore = sr * a.sre - si * a.sim, oim = sr * a.sim + si * a.sre;
-            u[g] = make_double2(ore, oim);
-            if (acc != nullptr && (g & a.cmask) == a.cmask) {
-                const double2 o = acc[g];
-                acc[g] = make_double2(o.x + ore, o.y + oim);
-                red += ore * ore + oim * oim;
+#pragma unroll
+                for (int e = 0; e < kTileElems; ++e)
+                    if (FULL || e < n_e) u[g0 | goff_s[e]] = make_double2(re[e], im[e]);
+            } else {
+                double2 o[kTileElems];
+                bool on[kTileElems];
+#pragma unroll
+                for (int e = 0; e < kTileElems; ++e) {
+                    const uint64_t g = g0 | goff_s[e];
+                    on[e] = (FULL || e < n_e) && acc != nullptr && (g & a.cmask) == a.cmask;
+                    o[e] = on[e] ? acc[g] : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int e = 0; e < kTileElems; ++e) {
+                    if (!(FULL || e < n_e)) continue;
+                    const uint64_t g = g0 | goff_s[e];
+                    const double ore = re[e] * a.sre - im[e] * a.sim, oim = re[e] * a.sim + im[e] * a.sre;
+                    u[g] = make_double2(ore, oim);
+                    if (on[e]) {
+                        acc[g] = make_double2(o[e].x + ore, o[e].y + oim);
+                        red += ore * ore + oim * oim;
+                    }
+                }
             }
         }
         __syncthreads();  // everybody is done with this buffer and with coef_s / w_out_s
@@ -1383,18 +1675,23 @@ int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, c
     constexpr int THREADS = 256;
     const size_t smem = 2 * (sizeof(double2) << a.T);  // double-buffered tile
     static bool configured = false;
+    static int ctas_per_sm = 3;  // 3: <= 80 registers per thread (a few spills);  2: 128 registers
     if (!configured) {
-        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        if (const char* e = std::getenv("PQB_PAULI_CTAS_PER_SM")) ctas_per_sm = std::atoi(e) == 2 ? 2 : 3;
         configured = true;
     }
     uint64_t grid = a.n_tiles;
-    if (grid > 148 * 3) grid = 148 * 3;  // 3 resident CTAs per SM (64 KB of shared memory and <= 64 registers per thread each)
+    if (grid > uint64_t(148 * ctas_per_sm)) grid = 148 * ctas_per_sm;  // resident CTAs (64 KB of shared memory each)
     const bool reduce = a.expectation || (a.final && acc != nullptr);
-    if (a.T == kTileBits)
-        pauli_tile_kernel<THREADS, true><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+    if (a.T == kTileBits && ctas_per_sm == 3)
+        pauli_tile_kernel<THREADS, true, 3><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+    else if (a.T == kTileBits)
+        pauli_tile_kernel<THREADS, true, 2><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
     else
-        pauli_tile_kernel<THREADS, false><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+        pauli_tile_kernel<THREADS, false, 3><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
     launched(c);
     return int(grid);
 }

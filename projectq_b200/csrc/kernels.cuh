@@ -158,9 +158,12 @@ struct PauliTileArgs {
     uint64_t z_out[kTileTerms];     // z bits outside the tile (index positions)
     uint32_t xl[kTileTerms];        // xmask in tile coordinates (0 for a diagonal term)
     uint32_t zl[kTileTerms];        // z bits inside the tile, in tile coordinates
-    int n_terms;
-    int any_zl;                     // 0: no term of this launch has z bits inside the tile (no per-amplitude signs)
-    int all_real;                   // 1: every coefficient of this launch is real
+    uint8_t general[kTileTerms];    // 0: real coefficient and no z bit inside the tile (2 DFMA per amplitude, no sign work)
+    // The terms are ordered by where their partner amplitude is found: [0, n_reg) flip only the tile-coordinate bits that
+    // number a thread's own elements (the partner is in the thread's registers), the rest read it from the shared tile
+    // (diagonal terms with z bits on both sides of the tile boundary are the case xl = 0).  The constant factor
+    // (-1)^{popcount(xl & zl)} of the source-index sign is folded into coef by the host.
+    int n_terms, n_reg;
     double2 coef_outside[kTileTerms];  // diagonal terms with z entirely outside the tile
     uint64_t z_outside[kTileTerms];
     int n_outside;
