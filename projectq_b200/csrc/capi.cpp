@@ -587,7 +587,7 @@ int pqb_host_plan_pauli_tiles(const uint64_t* xmasks, const uint64_t* zmasks, si
         if (n_local_bits < 0 || n_local_bits > 62) return PQB_ERR_VALUE;
         std::vector<pqb::k::PauliTerm> terms(n_terms);
         for (size_t i = 0; i < n_terms; ++i) terms[i] = pqb::k::PauliTerm{xmasks[i], zmasks[i], 1.0 + double(i), 0.0};
-        const pqb::PauliPlan plan = pqb::plan_pauli_tiles(terms, n_local_bits);
+        const pqb::PauliPlan plan = pqb::plan_pauli_tiles(terms, n_local_bits, pqb::pauli_block_bits());
         for (size_t i = 0; i < n_terms; ++i) out_launch_of_term[i] = plan.launch_of_term[i];
         if (out_n_launches) *out_n_launches = plan.launches.size();
         for (size_t l = 0; l < plan.launches.size() && l < cap_launches; ++l) out_tile_masks[l] = plan.tile_mask[l];

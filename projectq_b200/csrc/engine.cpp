@@ -58,6 +58,7 @@ Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
     // only the state buffer reserves its address range now; the two scratch buffers do so on first use (ensure_scratch)
     state_->init(device_, /*exportable=*/world_ > 1);
     PQB_CHECK(cudaMalloc(&d_partials_, sizeof(double) * k::kReducePartials));
+    PQB_CHECK(cudaMalloc(&d_pauli_sync_, sizeof(unsigned) * k::kPauliSyncWords));
     PQB_CHECK(cudaMalloc(&d_scalars_, sizeof(double) * kScalarDoubles));
     PQB_CHECK(cudaMallocHost(&h_pinned_, sizeof(double) * kScalarDoubles));
 
@@ -87,6 +88,7 @@ Engine::~Engine() {
     for (auto e : free_events_) cudaEventDestroy(e);
     dist_.reset();
     if (d_partials_) cudaFree(d_partials_);
+    if (d_pauli_sync_) cudaFree(d_pauli_sync_);
     if (d_scalars_) cudaFree(d_scalars_);
     if (h_pinned_) cudaFreeHost(h_pinned_);
     if (d_small_) cudaFree(d_small_);
@@ -1275,8 +1277,21 @@ std::vector<k::PauliTerm> Engine::build_terms(const TermsView& t, const uint32_t
 // in runs of at least 64 bytes) plus the bits that the most still-uncovered terms need; a term is applied by the first
 // launch whose tile bits contain its whole xmask (z factors are signs and never need a partner amplitude).  Terms whose
 // support is too large for any tile are returned in `wide` and go through per-term global gathers.
-PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
+int pauli_block_bits() {
+    static const int bits = [] {
+        const char* e = std::getenv("PQB_PAULI_BLOCK_BITS");
+        // Off by default: measured on TFIM-28 (profiles/r2_pauli_tile_history.md) the fused launch does keep the second
+        // read of the vector in L2 (DRAM reads 12.9 -> 10.3 GB per application) but the launches are bound by the shared-
+        // memory pipe, not by HBM, and the chained sets wait on one another: 8.4 ms instead of 7.6 ms per application.
+        const int b = e ? std::atoi(e) : 0;
+        return b < 0 ? 0 : (b > 40 ? 40 : b);
+    }();
+    return bits;
+}
+
+PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L, int block_bits) {
     PauliPlan plan;
+    plan.block_bits = block_bits;
     plan.launch_of_term.assign(terms.size(), -1);
     const int T = std::min(k::kTileBits, L);
     const uint64_t low2 = L >= 2 ? 3 : (L == 1 ? 1 : 0);
@@ -1357,6 +1372,9 @@ PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
             }
             long at = -1;
             if (first_chunk && !table.empty()) {
+                a.w_real = 1;
+                for (const double2& w : table)
+                    if (w.y != 0.0) a.w_real = 0;
                 at = long(plan.tables.size());
                 plan.tables.insert(plan.tables.end(), table.begin(), table.end());
             }
@@ -1366,26 +1384,35 @@ PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int L) {
             first_chunk = false;
         } while (at_g < generic.size() || at_o < outside.size());
     };
-    while (!todo.empty()) {
-        uint64_t S = low2 | terms[todo[0]].xmask;  // the oldest uncovered term always fits: progress is guaranteed
-        while (__builtin_popcountll(S) < T) {
-            int count[64] = {0};
-            for (int i : todo) {
-                const uint64_t extra = terms[i].xmask & ~S;
-                if (extra == 0 || __builtin_popcountll(S | terms[i].xmask) > T) continue;
-                for (uint64_t m = extra; m; m &= m - 1) ++count[__builtin_ctzll(m)];
+    // Sets whose tile bits all lie below block_bits come first: the engine runs them fused, block by block, and what one
+    // hands to the next stays in L2 (kernels.cuh PauliFusedArgs).  The sets that need higher bits follow.
+    const uint64_t below_block = block_bits > T && block_bits < L ? (uint64_t(1) << block_bits) - 1 : ~uint64_t(0);
+    auto cover = [&](std::vector<int>& todo, uint64_t allowed) {
+        while (!todo.empty()) {
+            uint64_t S = low2 | terms[todo[0]].xmask;  // the oldest uncovered term always fits: progress is guaranteed
+            while (__builtin_popcountll(S) < T) {
+                int count[64] = {0};
+                for (int i : todo) {
+                    const uint64_t extra = terms[i].xmask & ~S;
+                    if (extra == 0 || __builtin_popcountll(S | terms[i].xmask) > T) continue;
+                    for (uint64_t m = extra; m; m &= m - 1) ++count[__builtin_ctzll(m)];
+                }
+                int best = -1;
+                for (int b = 0; b < L; ++b)
+                    if (((allowed >> b) & 1) && count[b] > 0 && (best < 0 || count[b] > count[best])) best = b;
+                if (best < 0) break;
+                S |= uint64_t(1) << best;
             }
-            int best = -1;
-            for (int b = 0; b < L; ++b)
-                if (count[b] > 0 && (best < 0 || count[b] > count[best])) best = b;
-            if (best < 0) break;
-            S |= uint64_t(1) << best;
+            std::vector<int> members, rest;
+            for (int i : todo) ((terms[i].xmask & ~S) == 0 ? members : rest).push_back(i);
+            emit(S, members);
+            todo.swap(rest);
         }
-        std::vector<int> members, rest;
-        for (int i : todo) ((terms[i].xmask & ~S) == 0 ? members : rest).push_back(i);
-        emit(S, members);
-        todo.swap(rest);
-    }
+    };
+    std::vector<int> inside, beyond;
+    for (int i : todo) ((terms[i].xmask & ~below_block) == 0 ? inside : beyond).push_back(i);
+    cover(inside, below_block);
+    cover(beyond, ~uint64_t(0));
     if (plan.launches.empty()) emit(low2, {});  // no tile-able term: an empty launch still finalises (scale / accumulate)
     return plan;
 }
@@ -1439,11 +1466,21 @@ double Engine::get_expectation_value(const TermsView& t, const uint32_t* ids, si
         PauliProgram prog = build_pauli_program(batch);  // the batch's X/Y support is on-device: one group, this rank's shard
         if (prog.reads_peers()) throw RuntimeErr("internal: X on a rank bit was not remapped");
         PauliPlan& plan = prog.groups[0].plan;
-        for (auto& a : plan.launches) {
-            if (a.n_terms == 0 && a.n_outside == 0 && a.w_in == nullptr) continue;
-            a.expectation = 1;
-            const int grid = k::pauli_tile_pass(ctx(), psi(), nullptr, nullptr, a, d_partials_);
-            k::reduce_partials(ctx(), d_partials_, grid, d_acc, true);
+        // consecutive fusable launches go out as one; an empty launch (nothing but a finalisation) is skipped
+        for (size_t i = 0; i < plan.launches.size();) {
+            k::PauliTileArgs& a = plan.launches[i];
+            if (a.n_terms == 0 && a.n_outside == 0 && a.w_in == nullptr) {
+                ++i;
+                continue;
+            }
+            size_t j = i;
+            for (; j < plan.launches.size(); ++j) {
+                k::PauliTileArgs& b = plan.launches[j];
+                if (b.n_terms == 0 && b.n_outside == 0 && b.w_in == nullptr) break;
+                b.expectation = 1;
+            }
+            run_tile_launches(plan, i, j, psi(), nullptr, nullptr, d_acc);
+            i = j;
         }
         size_t i = 0;
         while (i < plan.wide.size()) {
@@ -1498,7 +1535,7 @@ Engine::PauliProgram Engine::build_pauli_program(const std::vector<k::PauliTerm>
         g.xr = it->first;
         std::stable_sort(it->second.begin(), it->second.end(),
                          [](const k::PauliTerm& a, const k::PauliTerm& b) { return a.xmask < b.xmask; });
-        g.plan = plan_pauli_tiles(it->second, L_);
+        g.plan = plan_pauli_tiles(it->second, L_, pauli_block_bits());
         prog.groups.push_back(std::move(g));
     }
     // tables and wide terms of every group go to the device in one upload
@@ -1560,6 +1597,8 @@ void Engine::run_pauli_program(PauliProgram& prog, const std::vector<const doubl
             k::pauli_gather_accumulate(ctx(), src[gi], u, local_amps(), plan.d_wide, int(plan.wide.size()), first);
             first = false;
         }
+        // flags first, then the launches (consecutive fusable ones as one launch)
+        std::vector<size_t> live;
         for (size_t i = 0; i < plan.launches.size(); ++i) {
             k::PauliTileArgs& a = plan.launches[i];
             if (!last_group && a.n_terms == 0 && a.n_outside == 0 && a.w_in == nullptr) continue;  // nothing to add
@@ -1569,10 +1608,38 @@ void Engine::run_pauli_program(PauliProgram& prog, const std::vector<const doubl
             a.sre = sre;
             a.sim = sim;
             a.cmask = cmask;
-            const int grid = k::pauli_tile_pass(ctx(), src[gi], u, a.final ? acc : nullptr, a, d_partials_);
-            if (a.final && acc != nullptr && d_norm != nullptr) k::reduce_partials(ctx(), d_partials_, grid, d_norm, false);
             first = false;
+            live.push_back(i);
         }
+        for (size_t p = 0; p < live.size();) {
+            size_t q = p + 1;
+            while (q < live.size() && live[q] == live[q - 1] + 1) ++q;  // a run of consecutive launches
+            const bool finalises = plan.launches[live[q - 1]].final != 0;
+            run_tile_launches(plan, live[p], live[q - 1] + 1, src[gi], u, finalises ? acc : nullptr, d_norm);
+            p = q;
+        }
+    }
+}
+
+// d_sum: expectation launches add their <psi|.|psi> contributions to it; a finalising launch with an accumulator overwrites
+// it with the squared norm of what it added
+void Engine::run_tile_launches(PauliPlan& plan, size_t first, size_t last, const double2* in, double2* u, double2* acc,
+                               double* d_sum) {
+    for (size_t i = first; i < last;) {
+        size_t j = i + 1;
+        if (plan.fusable(i, L_))
+            while (j < last && j - i < size_t(k::kTileSets) && plan.fusable(j, L_)) ++j;
+        const k::PauliTileArgs& tail = plan.launches[j - 1];
+        double2* acc_here = tail.final ? acc : nullptr;
+        const int grid = k::pauli_tile_pass(ctx(), in, u, acc_here, &plan.launches[i], int(j - i), plan.block_bits, d_partials_,
+                                            d_pauli_sync_);
+        if (d_sum != nullptr) {
+            if (tail.expectation)
+                k::reduce_partials(ctx(), d_partials_, grid, d_sum, true);
+            else if (tail.final && acc_here != nullptr)
+                k::reduce_partials(ctx(), d_partials_, grid, d_sum, false);
+        }
+        i = j;
     }
 }
 

@@ -78,8 +78,14 @@ struct PauliPlan {
     std::vector<k::PauliTerm> wide;
     std::vector<int> launch_of_term;         // per input term: the launch that applies it, -1 = wide
     const k::PauliTerm* d_wide = nullptr;
+    int block_bits = 0;                      // launches whose tile bits all lie below this bit may run fused (0: none)
+    bool fusable(size_t i, int n_local_bits) const {
+        return block_bits > 0 && (n_local_bits <= block_bits || (tile_mask[i] >> block_bits) == 0);
+    }
 };
-PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int n_local_bits);
+// block size (log2 amplitudes) of the fused, L2-resident execution of tile-bit sets; PQB_PAULI_BLOCK_BITS overrides (0 = off)
+int pauli_block_bits();
+PauliPlan plan_pauli_tiles(const std::vector<k::PauliTerm>& terms, int n_local_bits, int block_bits);
 
 class Engine {
 public:
@@ -180,6 +186,8 @@ private:
     };
     PauliProgram build_pauli_program(const std::vector<k::PauliTerm>& logical_terms);
     std::vector<const double2*> pauli_sources(const PauliProgram& prog, const GrowBuffer& buf);
+    // the tile launches [first, last) of one plan, consecutive fusable ones in one launch
+    void run_tile_launches(PauliPlan& plan, size_t first, size_t last, const double2* in, double2* u, double2* acc, double* d_sum);
     void run_pauli_program(PauliProgram& prog, const std::vector<const double2*>& src, double2* u, double sre, double sim,
                            double2* acc, uint64_t cmask, double* d_norm);
     void check_exchange_error();
@@ -210,6 +218,7 @@ private:
     GrowBuffer* scratch1_ = &buf_[1];
     GrowBuffer* scratch2_ = &buf_[2];
     double* d_partials_ = nullptr;         // kReducePartials doubles
+    unsigned* d_pauli_sync_ = nullptr;     // kPauliSyncWords words: ticket and block counters of the fused Pauli launches
     double* d_scalars_ = nullptr;          // small device scratch (bins, accumulators)
     double* h_pinned_ = nullptr;           // pinned host mirror of d_scalars_
     void* d_small_ = nullptr;              // terms / indices / tables upload area

@@ -1458,56 +1458,133 @@ constexpr int kTileElems = 8;  // 2^kTileBits / 256 threads
 // FULL: the tile has exactly kTileElems * THREADS amplitudes (every state of kTileBits or more local bits), so the element
 // loops carry no guards; the other instantiation serves tiny states.  Shared memory is addressed through 32-bit shared
 // addresses (ld.shared): with generic pointers the compiler re-derived the shared window for every load.
-template <int THREADS, bool FULL, int MINB>
+//
+// One launch runs up to kTileSets tile-bit sets ("fused" sets) whose tile bits all lie below f.block_bits: the state is
+// walked block by block (2^block_bits amplitudes), set 0 then set 1 ... of a block, so the vector being read and the partial
+// sums written by one set are still in L2 when the next set of the same block reads them — the partial-sum traffic between
+// fused sets never reaches HBM.  Work items (set, tile) are handed out in that order by a global ticket counter; an item of
+// set s > 0 may only touch the partial sums once every tile of set s-1 of its block has finished, which a per-block counter
+// signals.  A CTA never waits on a ticket larger than its own, so the smallest unfinished ticket always makes progress.
+// FUSED = false: a single set; its tiles are dealt out round-robin (no tickets, no counters).
+template <int THREADS, bool FULL, int MINB, bool FUSED>
 __global__ void __launch_bounds__(THREADS, MINB) pauli_tile_kernel(const double2* __restrict__ in, double2* __restrict__ u,
                                                                 double2* __restrict__ acc,
-                                                                const __grid_constant__ PauliTileArgs a,
-                                                                double* __restrict__ partials) {
+                                                                const __grid_constant__ PauliFusedArgs f,
+                                                                double* __restrict__ partials, unsigned* __restrict__ sync) {
     extern __shared__ double2 tile_buffers[];  // two tiles: the next one streams in (cp.async) while this one is used
     __shared__ double2 coef_s[kTileTerms];  // coefficients with this tile's outside-z sign applied
     __shared__ double2 w_out_s;             // sum of the outside-only diagonal terms for this tile
-    __shared__ uint64_t goff_s[kTileElems]; // index bits contributed by the element number e (the same for every thread)
-    __shared__ uint64_t base_s[3];          // index bits of the current tile, the next one and the one after: spreading a tile
-                                            // number over the non-tile bits costs a few hundred instructions, so ONE thread
-                                            // does it, two tiles ahead, instead of every warp
-    const uint32_t tile_amps = 1u << a.T;
+    __shared__ uint64_t goff_s[kTileSets][kTileElems];  // index bits contributed by the element number e (the same for every thread)
+    // the current work item, the next one and the one after: taking a ticket and spreading the tile number over the non-tile
+    // bits costs a global atomic and a few hundred instructions, so ONE thread does it, two items ahead
+    struct Item {
+        uint64_t base;   // index bits of the tile
+        uint32_t block;  // which block it belongs to
+        int set;         // < 0: no more work
+    };
+    __shared__ Item item_s[3];
+    const int T = f.set[0].T;  // (the same for every set of a launch)
+    const uint32_t tile_amps = 1u << T;
     constexpr int LOG_THREADS = THREADS == 256 ? 8 : 7;
     const int n_e = FULL ? kTileElems : (tile_amps > uint32_t(THREADS) ? int(tile_amps / THREADS) : 1);
-    auto coord_to_index = [&](uint32_t t) {
-        const uint32_t lo_mask = (1u << a.T_lo) - 1;
-        return uint64_t(t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
-    };
-    if (threadIdx.x < kTileElems) goff_s[threadIdx.x] = coord_to_index((uint32_t(threadIdx.x) << LOG_THREADS) & (tile_amps - 1));
-    const uint64_t g_tid = coord_to_index(threadIdx.x & (tile_amps - 1));
+    constexpr int SETS = FUSED ? kTileSets : 1;
+    const int n_sets = FUSED ? f.n_sets : 1;
+    uint64_t g_tid_set[SETS];
+#pragma unroll
+    for (int s = 0; s < SETS; ++s) {
+        g_tid_set[s] = 0;
+        if (s < n_sets) {
+            const PauliTileArgs& a = f.set[s];
+            auto coord_to_index = [&](uint32_t t) {
+                const uint32_t lo_mask = (1u << a.T_lo) - 1;
+                return uint64_t(t & lo_mask) | deposit_bits(uint64_t(t) >> a.T_lo, a.tile_pos + a.T_lo, a.T - a.T_lo);
+            };
+            if (threadIdx.x < kTileElems)
+                goff_s[s][threadIdx.x] = coord_to_index((uint32_t(threadIdx.x) << LOG_THREADS) & (tile_amps - 1));
+            g_tid_set[s] = coord_to_index(threadIdx.x & (tile_amps - 1));
+        }
+    }
+    auto g_tid_of = [&](int s) { return !FUSED || s == 0 ? g_tid_set[0] : (s == 1 ? g_tid_set[SETS > 1 ? 1 : 0] : g_tid_set[SETS > 2 ? 2 : 0]); };
     const bool mine = FULL || threadIdx.x < tile_amps;  // tiles smaller than the CTA (tiny states): the other threads idle
     const uint32_t buffers_s = smem_addr(tile_buffers), t16 = threadIdx.x * 16;
+    // Work items are produced by one thread, two items ahead.  Fused launches take tickets from a global counter; the atomic
+    // is fired one item before its result is decoded, so its latency never sits in front of a barrier.
+    const uint64_t tpb = f.tiles_per_block;
+    const int tpb_log2 = 63 - __clzll((long long)tpb);  // (a power of two in fused launches)
+    const uint64_t total_slots = (f.n_blocks + uint64_t(f.lag) * uint64_t(n_sets - 1)) * uint64_t(n_sets);
+    uint64_t next_static = blockIdx.x;  // FUSED = false: tile numbers blockIdx.x, + gridDim.x, ...
+    unsigned pending = 0;               // FUSED: the ticket taken last, not yet decoded
+    auto take = [&]() { pending = atomicAdd(&sync[0], 1u); };
+    auto decode = [&](Item& it) {  // -> the next work item
+        if (!FUSED) {
+            it.set = next_static < f.set[0].n_tiles ? 0 : -1;
+            it.block = 0;
+            it.base = insert_zero_bits(next_static, f.set[0].tile_pos, T);
+            next_static += gridDim.x;
+            return;
+        }
+        for (;;) {
+            const uint64_t ticket = pending;
+            const uint64_t slot = ticket >> tpb_log2, w = ticket & (tpb - 1);
+            if (slot >= total_slots) {
+                it.set = -1;
+                return;  // (no further ticket is taken: `pending` stays past the end)
+            }
+            take();
+            const int s = int(uint32_t(slot) % uint32_t(n_sets));
+            const long long b = (long long)(uint32_t(slot) / uint32_t(n_sets)) - (long long)(s) * f.lag;
+            if (b < 0 || uint64_t(b) >= f.n_blocks) continue;  // set s has not started yet / is already through
+            it.set = s;
+            it.block = uint32_t(b);
+            it.base = insert_zero_bits((uint64_t(b) << tpb_log2) + w, f.set[s].tile_pos, T);
+            return;
+        }
+    };
     if (threadIdx.x == 32 % THREADS) {
-        base_s[0] = insert_zero_bits(blockIdx.x, a.tile_pos, a.T);
-        base_s[1] = insert_zero_bits(uint64_t(blockIdx.x) + gridDim.x, a.tile_pos, a.T);
+        if (FUSED) take();
+        decode(item_s[0]);
+        decode(item_s[1]);
     }
-    __syncthreads();                            // goff_s, base_s
+    __syncthreads();                            // goff_s, item_s
     // asynchronous copy of one tile into one of the two buffers (16 bytes per thread and element, L2 -> shared directly)
-    auto fetch = [&](uint64_t tile_base, int buf) {
-        const uint64_t g0f = tile_base | g_tid;
+    auto fetch = [&](const Item& it, int buf) {
+        const int set = FUSED ? it.set : 0;
+        const uint64_t g0f = it.base | g_tid_of(set);
         double2* dst = tile_buffers + size_t(buf) * tile_amps;
 #pragma unroll
         for (int e = 0; e < kTileElems; ++e)
             if ((FULL || e < n_e) && mine)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + e * THREADS + threadIdx.x)),
-                             "l"(in + (g0f | goff_s[e]))
+                             "l"(in + (g0f | goff_s[set][e]))
                              : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // With two CTAs per SM (128 registers) and a single set, a thread keeps its slice of the diagonal table for the whole
+    // launch: its eight tile coordinates are the same in every tile.
+    constexpr bool ROOMY = MINB <= 2;
+    const bool hoisted = ROOMY && !FUSED;
+    double wtab_re[kTileElems];  // (the imaginary parts, rare for a Hermitian operator's diagonal, are re-read per tile)
+#pragma unroll
+    for (int e = 0; e < kTileElems; ++e)
+        wtab_re[e] = (hoisted && f.set[0].w_in != nullptr && (FULL || (e < n_e && mine)))
+                         ? __ldg(&f.set[0].w_in[e * THREADS + threadIdx.x].x)
+                         : 0.0;
     double red = 0.0;
     int buf = 0;
-    int slot = 0;  // base_s[slot] belongs to the current tile
-    if (uint64_t(blockIdx.x) < a.n_tiles) fetch(base_s[0], 0);
-    for (uint64_t tid_tile = blockIdx.x; tid_tile < a.n_tiles; tid_tile += gridDim.x, buf ^= 1, slot = slot == 2 ? 0 : slot + 1) {
-        const uint64_t base = base_s[slot];
+    int slot = 0;  // item_s[slot] is the current item
+    Item cur = item_s[0];
+    if (cur.set >= 0) fetch(cur, 0);
+    for (; cur.set >= 0; buf ^= 1, slot = slot == 2 ? 0 : slot + 1) {
+        const int set = FUSED ? cur.set : 0;
+        const PauliTileArgs& a = f.set[set];
+        const uint64_t base = cur.base;
+        const uint64_t g_tid = g_tid_of(set);
+        const uint64_t* goff = goff_s[set];
         const uint32_t tile_s = buffers_s + uint32_t(buf) * (tile_amps * 16);  // shared address of this tile
         auto at = [&](int e, uint32_t x16) { return lds_d2(tile_s + ((uint32_t(e) * (THREADS * 16) + t16) ^ x16)); };
-        const bool more = tid_tile + gridDim.x < a.n_tiles;
-        if (more) fetch(base_s[slot == 2 ? 0 : slot + 1], buf ^ 1);  // the other buffer was released by the barrier that ended the last tile
+        const Item nxt = item_s[slot == 2 ? 0 : slot + 1];
+        const bool more = nxt.set >= 0;
+        if (more) fetch(nxt, buf ^ 1);  // the other buffer was released by the barrier that ended the last tile
         if (int(threadIdx.x) < a.n_terms) {
             double2 c = a.coef[threadIdx.x];
             if (__popcll(base & a.z_out[threadIdx.x]) & 1) c = make_double2(-c.x, -c.y);
@@ -1528,7 +1605,7 @@ __global__ void __launch_bounds__(THREADS, MINB) pauli_tile_kernel(const double2
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 32 % THREADS)  // (this slot was last read before the barrier that ended the previous tile)
-            base_s[slot == 0 ? 2 : slot - 1] = insert_zero_bits(tid_tile + 2 * uint64_t(gridDim.x), a.tile_pos, a.T);
+            decode(item_s[slot == 0 ? 2 : slot - 1]);
         const uint64_t g0 = base | g_tid;
         double re[kTileElems] = {}, im[kTileElems] = {};
         const double2 w_out = w_out_s;
@@ -1553,11 +1630,15 @@ __global__ void __launch_bounds__(THREADS, MINB) pauli_tile_kernel(const double2
                 if ((FULL || e < n_e) && mine) {
                     const uint32_t t = e * THREADS + threadIdx.x;
                     self[e] = at(e, 0);
-                    double wr = w_out.x, wi = w_out.y;
+                    double wr = w_out.x + wtab_re[e], wi = w_out.y;
                     if (a.w_in != nullptr) {
-                        const double2 w = __ldg(a.w_in + t);
-                        wr += w.x;
-                        wi += w.y;
+                        if (!hoisted) {
+                            const double2 w = __ldg(a.w_in + t);
+                            wr += w.x;
+                            wi += w.y;
+                        } else if (!a.w_real) {
+                            wi += __ldg(&a.w_in[t].y);
+                        }
                     }
                     re[e] = wr * self[e].x - wi * self[e].y;
                     im[e] = wr * self[e].y + wi * self[e].x;
@@ -1622,46 +1703,64 @@ __global__ void __launch_bounds__(THREADS, MINB) pauli_tile_kernel(const double2
                 const double2 self = at(e, 0);
                 red += self.x * re[e] + self.y * im[e];  // Re(conj(psi_j) s_j)
             }
-        } else if (mine) {
-            // all loads of the partial sums (and of the accumulator) are in flight before the first store
-            if (!a.first) {
-                double2 prev[kTileElems];
-#pragma unroll
-                for (int e = 0; e < kTileElems; ++e)
-                    prev[e] = (FULL || e < n_e) ? __ldcg(u + (g0 | goff_s[e])) : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int e = 0; e < kTileElems; ++e) {
-                    re[e] += prev[e].x;
-                    im[e] += prev[e].y;
+        } else {
+            // a fused set s > 0 continues the partial sums of set s-1: every tile of that set in this block must be through
+            const bool chained = FUSED && set > 0;
+            if (chained) {
+                if (threadIdx.x == 0) {
+                    const unsigned need = unsigned(set) * unsigned(f.tiles_per_block);
+                    unsigned seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync + 1 + cur.block) : "memory");
+                        if (seen < need) __nanosleep(100);
+                    } while (seen < need);
                 }
+                __syncthreads();
             }
-            if (!a.final) {
+            if (mine) {
+                // all loads of the partial sums (and of the accumulator) are in flight before the first store
+                if (!a.first) {
+                    double2 prev[kTileElems];
 #pragma unroll
-                for (int e = 0; e < kTileElems; ++e)
-                    if (FULL || e < n_e) u[g0 | goff_s[e]] = make_double2(re[e], im[e]);
-            } else {
-                double2 o[kTileElems];
-                bool on[kTileElems];
+                    for (int e = 0; e < kTileElems; ++e)
+                        prev[e] = (FULL || e < n_e) ? __ldcg(u + (g0 | goff[e])) : make_double2(0.0, 0.0);
 #pragma unroll
-                for (int e = 0; e < kTileElems; ++e) {
-                    const uint64_t g = g0 | goff_s[e];
-                    on[e] = (FULL || e < n_e) && acc != nullptr && (g & a.cmask) == a.cmask;
-                    o[e] = on[e] ? acc[g] : make_double2(0.0, 0.0);
+                    for (int e = 0; e < kTileElems; ++e) {
+                        re[e] += prev[e].x;
+                        im[e] += prev[e].y;
+                    }
                 }
+                if (!a.final) {
 #pragma unroll
-                for (int e = 0; e < kTileElems; ++e) {
-                    if (!(FULL || e < n_e)) continue;
-                    const uint64_t g = g0 | goff_s[e];
-                    const double ore = re[e] * a.sre - im[e] * a.sim, oim = re[e] * a.sim + im[e] * a.sre;
-                    u[g] = make_double2(ore, oim);
-                    if (on[e]) {
-                        acc[g] = make_double2(o[e].x + ore, o[e].y + oim);
-                        red += ore * ore + oim * oim;
+                    for (int e = 0; e < kTileElems; ++e)
+                        if (FULL || e < n_e) __stcg(u + (g0 | goff[e]), make_double2(re[e], im[e]));
+                } else {
+                    double2 o[kTileElems];
+                    bool on[kTileElems];
+#pragma unroll
+                    for (int e = 0; e < kTileElems; ++e) {
+                        const uint64_t g = g0 | goff[e];
+                        on[e] = (FULL || e < n_e) && acc != nullptr && (g & a.cmask) == a.cmask;
+                        o[e] = on[e] ? acc[g] : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int e = 0; e < kTileElems; ++e) {
+                        if (!(FULL || e < n_e)) continue;
+                        const uint64_t g = g0 | goff[e];
+                        const double ore = re[e] * a.sre - im[e] * a.sim, oim = re[e] * a.sim + im[e] * a.sre;
+                        u[g] = make_double2(ore, oim);
+                        if (on[e]) {
+                            acc[g] = make_double2(o[e].x + ore, o[e].y + oim);
+                            red += ore * ore + oim * oim;
+                        }
                     }
                 }
             }
+            if (FUSED && set + 1 < n_sets) __threadfence();  // the partial sums are visible before the block counter moves
         }
         __syncthreads();  // everybody is done with this buffer and with coef_s / w_out_s
+        if (FUSED && !a.expectation && set + 1 < n_sets && threadIdx.x == 0) atomicAdd(sync + 1 + cur.block, 1u);
+        cur = nxt;
     }
     if (partials != nullptr) {
         red = block_sum(red);
@@ -1669,29 +1768,60 @@ __global__ void __launch_bounds__(THREADS, MINB) pauli_tile_kernel(const double2
     }
 }
 
-int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs& a, double* d_partials) {
-    if (a.T > kTileBits || a.T < 0 || a.n_terms > kTileTerms || a.n_outside > kTileTerms)
-        throw std::invalid_argument("pauli_tile_pass: bad arguments");
+int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs* sets, int n_sets,
+                    int block_bits, double* d_partials, unsigned* d_sync) {
+    if (n_sets < 1 || n_sets > kTileSets) throw std::invalid_argument("pauli_tile_pass: bad number of sets");
+    PauliFusedArgs f;
+    for (int s = 0; s < n_sets; ++s) {
+        const PauliTileArgs& a = sets[s];
+        if (a.T > kTileBits || a.T < 0 || a.n_terms > kTileTerms || a.n_outside > kTileTerms || a.T != sets[0].T ||
+            a.n_tiles != sets[0].n_tiles || a.expectation != sets[0].expectation)
+            throw std::invalid_argument("pauli_tile_pass: bad arguments");
+        f.set[s] = a;
+    }
+    const PauliTileArgs& a0 = sets[0];
+    const PauliTileArgs& last = sets[n_sets - 1];
+    f.n_sets = n_sets;
+    f.lag = 1;
+    f.tiles_per_block = a0.n_tiles;
+    f.n_blocks = 1;
+    if (n_sets > 1 && block_bits > a0.T && (a0.n_tiles >> (block_bits - a0.T)) > 1) {
+        f.tiles_per_block = uint64_t(1) << (block_bits - a0.T);
+        f.n_blocks = a0.n_tiles / f.tiles_per_block;
+    }
+    if (1 + f.n_blocks > uint64_t(kPauliSyncWords)) throw std::invalid_argument("pauli_tile_pass: too many blocks");
     constexpr int THREADS = 256;
-    const size_t smem = 2 * (sizeof(double2) << a.T);  // double-buffered tile
+    const size_t smem = 2 * (sizeof(double2) << a0.T);  // double-buffered tile
     static bool configured = false;
-    static int ctas_per_sm = 3;  // 3: <= 80 registers per thread (a few spills);  2: 128 registers
+    static int ctas_per_sm = 2;  // 2: 128 registers per thread (measured faster: 7.7 vs 8.9 ms per TFIM-28 operator);  3: <= 80, a few spills
     if (!configured) {
-        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        if (const char* e = std::getenv("PQB_PAULI_CTAS_PER_SM")) ctas_per_sm = std::atoi(e) == 2 ? 2 : 3;
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PQB_CUDA_CHECK(cudaFuncSetAttribute(pauli_tile_kernel<THREADS, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        if (const char* e = std::getenv("PQB_PAULI_CTAS_PER_SM")) ctas_per_sm = std::atoi(e) == 3 ? 3 : 2;
         configured = true;
     }
-    uint64_t grid = a.n_tiles;
-    if (grid > uint64_t(148 * ctas_per_sm)) grid = 148 * ctas_per_sm;  // resident CTAs (64 KB of shared memory each)
-    const bool reduce = a.expectation || (a.final && acc != nullptr);
-    if (a.T == kTileBits && ctas_per_sm == 3)
-        pauli_tile_kernel<THREADS, true, 3><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
-    else if (a.T == kTileBits)
-        pauli_tile_kernel<THREADS, true, 2><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+    const bool fused = n_sets > 1;
+    // ticket counter + one counter per block
+    if (fused) PQB_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, size_t(1 + f.n_blocks) * sizeof(unsigned), c.stream));
+    uint64_t grid = a0.n_tiles * uint64_t(n_sets);
+    const int resident = fused ? 2 : ctas_per_sm;
+    if (grid > uint64_t(148 * resident)) grid = 148 * resident;  // resident CTAs (64 KB of shared memory each)
+    const bool reduce = a0.expectation || (last.final && acc != nullptr);
+    double* part = reduce ? d_partials : nullptr;
+    const bool full = a0.T == kTileBits;
+    if (full && fused)
+        pauli_tile_kernel<THREADS, true, 2, true><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, f, part, d_sync);
+    else if (full && ctas_per_sm == 3)
+        pauli_tile_kernel<THREADS, true, 3, false><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, f, part, d_sync);
+    else if (full)
+        pauli_tile_kernel<THREADS, true, 2, false><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, f, part, d_sync);
+    else if (fused)
+        pauli_tile_kernel<THREADS, false, 3, true><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, f, part, d_sync);
     else
-        pauli_tile_kernel<THREADS, false, 3><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, a, reduce ? d_partials : nullptr);
+        pauli_tile_kernel<THREADS, false, 3, false><<<unsigned(grid), THREADS, smem, c.stream>>>(in, u, acc, f, part, d_sync);
     launched(c);
     return int(grid);
 }

@@ -168,6 +168,7 @@ struct PauliTileArgs {
     uint64_t z_outside[kTileTerms];
     int n_outside;
     const double2* w_in;            // sum of the diagonal terms with z inside the tile, per tile coordinate (or nullptr)
+    int w_real;                     // 1: every entry of w_in is real
     int T, T_lo;                    // tile bits; the lowest T_lo of them are the index bits 0..T_lo-1
     uint8_t tile_pos[16];           // ascending
     uint64_t n_tiles;
@@ -178,8 +179,22 @@ struct PauliTileArgs {
     double sre, sim;                // scale
     uint64_t cmask;                 // acc_j += u_j and norm += |u_j|^2 where (j & cmask) == cmask (final only, acc != nullptr)
 };
-// d_partials receives one double per CTA when `expectation` or (final && acc); grid size is returned
-int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs& a, double* d_partials);
+// One launch runs up to kTileSets sets back to back ("fused"): when their tile bits all lie below block_bits, the state is
+// walked block by block and the partial sums one set hands to the next stay in L2 (see pauli_tile_kernel).
+constexpr int kTileSets = 3;
+constexpr int kPauliSyncWords = (1 << 16) + 1;  // unsigned words of d_sync: a ticket counter + one counter per block
+struct PauliFusedArgs {
+    PauliTileArgs set[kTileSets];
+    int n_sets;
+    int lag;                   // blocks between a block's set s and its set s+1 in the ticket order
+    uint64_t tiles_per_block;  // per set
+    uint64_t n_blocks;
+};
+// d_partials receives one double per CTA when `expectation` or (final && acc); grid size is returned.  The sets must agree in
+// T, n_tiles and `expectation`; first / final describe the whole chain (set 0 may continue earlier launches, the last set may
+// finalise).  d_sync: kPauliSyncWords unsigned words of device scratch.
+int pauli_tile_pass(const Ctx& c, const double2* in, double2* u, double2* acc, const PauliTileArgs* sets, int n_sets,
+                    int block_bits, double* d_partials, unsigned* d_sync);
 void reduce_partials(const Ctx& c, const double* d_partials, int n, double* d_out, bool accumulate);
 // out[j] (+)= sum_t c_t (P_t in)[j] by per-term gathers from global memory (terms whose X support no tile covers)
 void pauli_gather_accumulate(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const PauliTerm* d_terms,

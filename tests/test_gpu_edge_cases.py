@@ -359,3 +359,59 @@ def test_generic_math_function_is_called_on_every_register_value_like_the_refere
     chk.emulate_math(f, [[0, 1, 2], [4]], [3])
     m1, v1 = gpu.cheat()
     assert np.array_equal(np.asarray(v1), np.asarray(chk.cheat()[1]))
+
+
+_OPT_IN_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+from oracle.statevec_oracle import OracleSimulator
+from projectq_b200.backend import SimulatorBackend
+from projectq_b200.workloads import tfim_terms
+from tests.helpers import brickwork_circuit, rand_unitary
+
+n = 16
+gpu, chk = SimulatorBackend(3), OracleSimulator(3)
+for q in range(n):
+    gpu.allocate_qubit(q)
+    chk.allocate_qubit(q)
+rng = np.random.default_rng(5)
+for m, t, c in brickwork_circuit(n, 3, seed=11):
+    gpu.apply_controlled_gate(m, t, c)
+    chk.apply_controlled_gate(m, t, c)
+for pos in ([3, 7, 9, 12], [4, 5, 6, 15], [8, 10, 11, 13]):   # k = 4 with the three lowest bits free
+    u = rand_unitary(rng, 4)
+    gpu.apply_controlled_gate(u, pos, [14] if 14 not in pos else [])
+    chk.apply_controlled_gate(u, pos, [14] if 14 not in pos else [])
+gpu.run()
+chk.run()
+terms = tfim_terms(n) + [([(0, "Y"), (9, "Z"), (15, "X")], 0.3), ([(12, "Z"), (13, "Z"), (2, "Z")], -0.2)]
+ids = list(range(n))
+e_gpu, e_chk = gpu.get_expectation_value(terms, ids), chk.get_expectation_value(terms, ids)
+assert abs(e_gpu - e_chk) < 1e-11, (e_gpu, e_chk)
+gpu.emulate_time_evolution(terms, 0.07, ids, [])
+chk.emulate_time_evolution(terms, 0.07, ids, [])
+cterms = [(t, c * (0.6 + 0.2j)) for t, c in terms]
+gpu.apply_qubit_operator(cterms, ids)
+chk.apply_qubit_operator(cterms, ids)
+err = float(np.max(np.abs(np.asarray(gpu.cheat()[1]) - chk.cheat()[1])))
+assert err < 1e-11, err
+print("opt-in paths OK", err)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"PQB_PAULI_BLOCK_BITS": "13"}, {"PQB_PAULI_BLOCK_BITS": "30"}, {"PQB_DENSE_DMMA": "1"},
+                                 {"PQB_DENSE_DMMA": "2"}, {"PQB_PAULI_CTAS_PER_SM": "3"}])
+def test_opt_in_kernel_paths_match_the_oracle(env):
+    """the measured-and-not-adopted kernel forms stay correct: tile-bit sets fused block by block (several blocks / one block),
+    the k = 4 pass on the FP64 tensor pipe (register and cp.async-ring form), the 3-CTA Pauli tile kernel"""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _OPT_IN_SCRIPT % root], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, **env), cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "opt-in paths OK" in out.stdout
