@@ -617,13 +617,20 @@ void Engine::run() {
         if (it == map_.end()) throw RuntimeErr("apply_controlled_gate(): Unknown qubit id. Please allocate the qubit first.");
         return loc_[it->second];
     };
-    // Relative cost of one pass by width, measured on B200 (profiles/): k <= 4 runs at the HBM roofline (32 B/amplitude),
-    // k = 5 is bound by the FP64 pipe (256 flop/amplitude) and takes ~2.4x as long, so a 5-wide pass only pays off when
-    // it swallows that many more gates.  A control bit halves the amplitudes a pass touches.
-    auto cost = [](const std::vector<Cluster>& cs) {
+    // Relative cost of one pass by width, measured on B200 (profiles/): k <= 4 runs at the HBM roofline (32 B/amplitude);
+    // k = 5 is bound by FP64 throughput (256 flop/amplitude): ~1.55x on the tensor pipe (DMMA kernel; sustained 9.2 ms against
+    // 5.85 ms at 30 qubits), ~2.4x with the DFMA kernel, so a 5-wide pass only pays off when it swallows that many more gates.
+    // A control bit halves the amplitudes a pass touches.
+    auto cost = [&](const std::vector<Cluster>& cs) {
         double c = 0.0;
         for (auto& cl : cs) {
-            double w = cl.width >= 5 ? 2.4 : 1.0;
+            double w = 1.0;
+            if (cl.width >= 5) {
+                uint64_t lowest = 64;
+                for (auto t : cl.targets) lowest = std::min(lowest, key(t));
+                for (auto q : cl.ctrls) lowest = std::min(lowest, key(q));
+                w = k::dense_k5_dmma_applies(L_, int(lowest), cl.width + cl.n_ctrl) ? 1.55 : 2.4;
+            }
             for (int i = 0; i < cl.n_ctrl && i < 6; ++i) w *= 0.5;
             c += w + 0.002;  // + launch overhead so tiny states prefer fewer passes
         }

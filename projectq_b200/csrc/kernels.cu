@@ -93,6 +93,7 @@ struct DenseArgs {
     int n_ins;
     uint8_t tpos[8];
     uint8_t ins_pos[64];
+    uint8_t free_lo[8];  // the lowest index bits that are neither target nor control / slice bit (64 = none left)
 };
 
 // 256-bit global accesses (sm_100 LDG.E.256 / STG.E.256): two adjacent amplitudes per lane, so every lane moves a full
@@ -503,6 +504,140 @@ static void launch_dense_k4_dmma_reg(const Ctx& c, double2* psi, const DenseArgs
     launched(c);
 }
 
+// k = 5 on the FP64 tensor pipe.  Unlike k = 4 this width is bound by FP64 throughput (256 flop per amplitude: the DFMA
+// kernel reaches 20-23 TFLOP/s, 60-68 % of the vector peak, with 168 registers and 64 KB of unrolled code), so here the
+// tensor pipe's 37 TFLOP/s at half the energy per flop is what counts and a ~5.7 ms memory path is enough.  Same mapping as
+// apply_dense_k4_dmma_reg_kernel with 8 row blocks x 16 k-steps: the complex 32x32 mat-vec as the real 64x64 product for 8
+// neighbouring amplitude groups per DMMA column block.  The 32 complex matrix entries a lane needs (U[m + 8h][kc + 4i],
+// h < 4, i < 8) do not fit in registers next to the data, so the CTA keeps the matrix in shared memory in fragment order
+// ([i][h][lane], one conflict-free LDS.128 per entry) and a lane re-reads the 4 entries of a k-step pair just before the 16
+// DMMAs that use them.  Persistent warps, Q batches (8 groups each) per step with all their loads in flight first.
+template <int Q, int THREADS, int MINB, bool GENERAL>
+__global__ void __launch_bounds__(THREADS, MINB) apply_dense_k5_dmma_kernel(double2* __restrict__ psi,
+                                                                      const __grid_constant__ DenseArgs<5> p) {
+    __shared__ double2 frag_s[8 * 4 * 32];  // 16 KB
+    const int lane = threadIdx.x & 31, kc = lane & 3, hi = lane >> 2;
+    for (int idx = threadIdx.x; idx < 8 * 4 * 32; idx += THREADS) {
+        const int l = idx & 31, h = (idx >> 5) & 3, i = idx >> 7;
+        frag_s[idx] = p.m[((l >> 2) + 8 * h) * 32 + (l & 3) + 4 * i];
+    }
+    __syncthreads();
+    const uint32_t frag0 = smem_addr(frag_s) + lane * 16;
+    uint64_t stride[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l) stride[l] = uint64_t(1) << p.tpos[l];
+    auto offset = [&](int j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+            if ((j >> l) & 1) off += stride[l];
+        return off;
+    };
+    // The 8 groups of a batch (and the Q batches of a step) are consecutive group numbers, so they differ in the LOWEST FREE
+    // index bits, wherever the targets are: group n of a batch sits at spread(n), spread = deposit onto the free bits.  With
+    // the three lowest index bits free that is n itself and the two groups a lane finishes are neighbours (one 256-bit store).
+    // GENERAL = false: the four lowest index bits are free, spread is the identity and every offset below is an immediate.
+    auto spread = [&](int g) {
+        if (!GENERAL) return uint64_t(g);
+        uint64_t off = 0;
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+            if ((g >> l) & 1) off += uint64_t(1) << p.free_lo[l];
+        return off;
+    };
+    const bool pair_adjacent = !GENERAL || p.free_lo[0] == 0;
+    const uint64_t off_in = offset(kc) + spread(hi), off_m = offset(hi) + spread(2 * kc), off_pair = spread(1);
+    uint64_t off_batch[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) off_batch[j] = spread(8 * j);
+    const uint64_t n_steps = p.n_items >> 3 >> Q_LOG2(Q);
+    const uint64_t n_warps = (uint64_t(gridDim.x) * THREADS) >> 5;
+    for (uint64_t step = (uint64_t(blockIdx.x) * THREADS + threadIdx.x) >> 5; step < n_steps; step += n_warps) {
+        const uint64_t b = insert_zero_bits(step << (3 + Q_LOG2(Q)), p.ins_pos, p.n_ins) | p.ctrl_mask;
+        const double2* src = psi + b + off_in;
+        double2 in[Q][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) in[j][i] = src[offset(4 * i) + (GENERAL ? off_batch[j] : uint64_t(8 * j))];
+        double2* dst0 = psi + b + off_m;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            double d[8][2];
+#pragma unroll
+            for (int rb = 0; rb < 8; ++rb) d[rb][0] = d[rb][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double2 a[4];  // U[m + 8h][kc + 4i], h = 0..3
+#pragma unroll
+                for (int h = 0; h < 4; ++h) a[h] = lds_d2(frag0 + (i * 4 + h) * (32 * 16));
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const double bv = part == 0 ? in[j][i].x : in[j][i].y;
+#pragma unroll
+                    for (int rb = 0; rb < 8; ++rb) {
+                        const int h = rb >> 1, po = rb & 1;
+                        const double av = po == part ? a[h].x : (po == 0 ? -a[h].y : a[h].y);
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(d[rb][0]), "+d"(d[rb][1])
+                                     : "d"(av), "d"(bv));
+                    }
+                }
+            }
+            double2* dst = dst0 + (GENERAL ? off_batch[j] : uint64_t(8 * j));
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                double2* o = dst + ((h & 1) ? stride[3] : 0) + ((h & 2) ? stride[4] : 0);
+                const double2 g0 = make_double2(d[2 * h][0], d[2 * h + 1][0]), g1 = make_double2(d[2 * h][1], d[2 * h + 1][1]);
+                if (pair_adjacent) {
+                    st256(o, g0, g1);
+                } else {  // (lanes m and m ^ 1 complete each other's sectors inside the same request)
+                    o[0] = g0;
+                    o[off_pair] = g1;
+                }
+            }
+        }
+    }
+}
+
+// PQB_DENSE_DMMA5: 0 = off (the DFMA kernel), 1 (default) = on
+static int dense_dmma5_variant() {
+    static const int u = [] {
+        const char* e = getenv("PQB_DENSE_DMMA5");
+        return e ? atoi(e) : 1;
+    }();
+    return u;
+}
+
+template <int Q, int THREADS, int MINB, bool GENERAL>
+static void launch_dense_k5_dmma_v(const Ctx& c, double2* psi, const DenseArgs<5>& args) {
+    const uint64_t warps = args.n_items >> 3 >> Q_LOG2(Q);
+    uint64_t blocks = (warps * 32 + THREADS - 1) / THREADS;
+    if (blocks > uint64_t(148 * MINB)) blocks = 148 * MINB;
+    apply_dense_k5_dmma_kernel<Q, THREADS, MINB, GENERAL><<<unsigned(blocks), THREADS, 0, c.stream>>>(psi, args);
+    launched(c);
+}
+
+// applies whenever a step (Q = 2 batches of 8 groups) exists; the lowest fixed bit only decides how the runs look
+bool dense_k5_dmma_applies(int n_bits, int lowest_fixed_bit, int n_fixed) {
+    (void)lowest_fixed_bit;
+    return dense_dmma5_variant() != 0 && n_bits - n_fixed >= 5;
+}
+
+static bool launch_dense_k5_dmma(const Ctx& c, double2* psi, int n_bits, const DenseArgs<5>& args) {
+    if (!dense_k5_dmma_applies(n_bits, args.ins_pos[0], args.n_ins)) return false;
+    const bool low4_free = args.free_lo[3] == 3;
+    // Measured at 30 qubits (profiles/r2_dense_k5_dmma.md): with the four lowest bits free the immediate-offset form at 3 CTAs
+    // of 128 threads per SM runs 8.8 ms per pass (9.6-10.0 at 2 CTAs); every other placement runs 8.3-8.6 ms with the general
+    // form at 2 CTAs and no register cap (~230 registers; 10.5-11.4 ms at 3 CTAs with spills, 8.8-9.1 with one batch per step
+    // at 88 registers and 5 CTAs).
+    if (low4_free)
+        launch_dense_k5_dmma_v<2, 128, 3, false>(c, psi, args);
+    else
+        launch_dense_k5_dmma_v<2, 128, 2, true>(c, psi, args);
+    return true;
+}
+
 // PQB_DENSE_DMMA: 0 (default) = off, 1 = register form, 2 = cp.async ring form.  Off by default because it measures SLOWER
 // than the DFMA kernel in the sustained benchmark even though it leaves power on the table: 6.00-6.05 ms per pass at
 // 1.60-1.62 GHz against 5.83 ms at 1.41 GHz on the same box (profiles/r2_dmma_experiment.md) — both forms stop at a memory
@@ -634,6 +769,15 @@ static void fill_dense_args(DenseArgs<K>& args, int n_bits, const uint8_t* tpos,
             args.ins_pos[n++] = fixed[b++];
     }
     args.n_ins = n;
+    {
+        int nf_lo = 0, at = 0;
+        for (int b = 0; b < n_bits && nf_lo < 8; ++b) {
+            while (at < n && args.ins_pos[at] < b) ++at;
+            if (at < n && args.ins_pos[at] == b) continue;
+            args.free_lo[nf_lo++] = uint8_t(b);
+        }
+        for (; nf_lo < 8; ++nf_lo) args.free_lo[nf_lo] = 64;
+    }
     args.ctrl_mask = cmask;
     for (int l = 0; l < K; ++l) args.tpos[l] = tpos[l];
     if (n > n_bits) throw std::invalid_argument("apply_dense: more target/control bits than state bits");
@@ -668,11 +812,17 @@ static void launch_dense(const Ctx& c, double2* psi, int n_bits, const uint8_t* 
         if constexpr (K == 4) {
             if (dense_tma_enabled() && tpos[1] == 1 && tpos[2] == 2 && tpos[3] == 3) return launch_dense_k4_low_tma(c, psi, args);
         }
+        if constexpr (K == 5) {
+            if (launch_dense_k5_dmma(c, psi, n_bits, args)) return;
+        }
         launch_dense_mode<K, 1, 1, (K >= 5 ? 128 : 256), (K == 3 ? 2 : (K <= 2 ? 4 : 3))>(c, psi, args);
     } else {
         fill_dense_args<K>(args, n_bits, tpos, n_ctrl, cpos, m_host, slice);
         if constexpr (K == 4) {
             if (launch_dense_k4_dmma(c, psi, n_bits, args)) return;
+        }
+        if constexpr (K == 5) {
+            if (launch_dense_k5_dmma(c, psi, n_bits, args)) return;
         }
         launch_dense_mode<K, 0, U0, T0, (K == 3 ? 2 : (K <= 2 ? 3 : 3))>(c, psi, args);
     }

@@ -29,6 +29,9 @@ constexpr int kReducePartials = 65536;  // capacity (in doubles) of the partial-
 void apply_dense(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl, const uint8_t* cpos,
                  const double* m_host, const Slice& slice = Slice());
 // Diagonal pass: psi[i] *= d[bits of i at tpos] on the control-satisfying subspace; d_host has 2^k (re,im) entries.
+// whether a k = 5 pass whose lowest target / control / slice bit is `lowest_fixed_bit` runs on the FP64 tensor pipe
+// (apply_dense_k5_dmma_kernel) rather than the DFMA kernel: the scheduler prices the two differently
+bool dense_k5_dmma_applies(int n_bits, int lowest_fixed_bit, int n_fixed);
 void apply_diagonal(const Ctx& c, double2* psi, int n_bits, int k, const uint8_t* tpos, int n_ctrl,
                     const uint8_t* cpos, const double* d_host, const Slice& slice = Slice());
 
