@@ -1219,6 +1219,65 @@ void Engine::emulate_math(int mode, int64_t a, int64_t N, const uint64_t* table,
         std::swap(state_, scratch1_);
         return;
     }
+    // Registers too wide to tabulate: the closed forms are inverted in closed form (kernels.cuh MathInverseDesc) whenever the
+    // gate's own preconditions hold — 0 <= a < N <= 2^bits for every register, gcd(a, N) = 1 for the multiplication.
+    if (mode != k::MATH_TABLE) {
+        bool ok = true;
+        unsigned long long a_sub = 0, barrett = 0;
+        if (mode == k::MATH_ADD) {
+            a_sub = (unsigned long long)a;
+        } else {
+            ok = a >= 0 && N > 0 && a < N;
+            for (size_t r = 0; r < n_regs && ok; ++r) {
+                const int nb = d.reg_off[r + 1] - d.reg_off[r];
+                if (nb < 63 && (unsigned long long)N > (1ull << nb)) ok = false;
+                if (nb >= 63) ok = false;
+            }
+            a_sub = (unsigned long long)a;
+            if (ok && mode == k::MATH_MUL_MOD) {
+                // a^-1 mod N by the extended Euclidean algorithm
+                long long r0 = N, r1 = a, t0 = 0, t1 = 1;
+                while (r1 != 0) {
+                    const long long q = r0 / r1;
+                    const long long r2 = r0 - q * r1, t2 = t0 - q * t1;
+                    r0 = r1, r1 = r2, t0 = t1, t1 = t2;
+                }
+                if (r0 != 1) {
+                    ok = false;  // not invertible: the map is not a permutation of [0, N)
+                } else {
+                    a_sub = (unsigned long long)(t0 < 0 ? t0 + N : t0);
+                    if ((unsigned long long)N < (1ull << 32)) barrett = ~0ull / (unsigned long long)N;  // floor((2^64 - 1) / N)
+                }
+            }
+        }
+        if (ok) {
+            k::MathInverseDesc g{};
+            g.mode = mode;
+            g.a_sub = a_sub;
+            g.N = (unsigned long long)N;
+            g.barrett = barrett;
+            g.ctrl_mask = d.ctrl_mask;
+            g.n_regs = int(n_regs);
+            int n_seg = 0;
+            for (size_t r = 0; r < n_regs; ++r) {
+                g.seg_off[r] = n_seg;
+                const size_t lo = size_t(d.reg_off[r]), hi = size_t(d.reg_off[r + 1]);
+                g.nb[r] = uint8_t(hi - lo);
+                for (size_t i = lo; i < hi;) {
+                    size_t j = i + 1;
+                    while (j < hi && d.reg_pos[j] == d.reg_pos[j - 1] + 1) ++j;
+                    g.seg[n_seg++] = {d.reg_pos[i], uint8_t(j - i), uint8_t(i - lo)};
+                    i = j;
+                }
+            }
+            g.seg_off[n_regs] = n_seg;
+            for (size_t i = 0; i < flat; ++i) g.reg_mask |= uint64_t(1) << d.reg_pos[i];
+            ensure_scratch(*scratch1_, bytes);
+            k::emulate_math_inverse(ctx(), psi(), scratch1_->amps(), local_amps(), g);
+            std::swap(state_, scratch1_);
+            return;
+        }
+    }
     if (mode == k::MATH_TABLE)
         d.d_table = static_cast<const unsigned long long*>(small_upload(table, table_len * sizeof(uint64_t)));
     ensure_scratch(*scratch1_, bytes);

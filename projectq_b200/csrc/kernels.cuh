@@ -129,6 +129,27 @@ struct MathGatherDesc {
 };
 void emulate_math_gather(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const MathGatherDesc& d);
 
+// Gather through the inverse map in CLOSED FORM, for registers too wide to tabulate.  Per register (nb bits, value y):
+//   x + a            : the single source (y - a) mod 2^nb;
+//   (x + a) % N      : y >= N has no source; y < N has x0 = (y - a) mod N and, from outside the gate's domain, x0 + k N < 2^nb;
+//   (x * a) % N      : the same with x0 = (y * a^-1) mod N  (needs gcd(a, N) = 1; Barrett reduction with m = floor(2^64 / N)).
+// The host checks 0 <= a < N <= 2^nb (and the gcd) and otherwise falls back to the atomic scatter.  Sources of several
+// registers combine as a product set; an output amplitude is the sum over it (one term whenever the state stays inside the
+// gate's domain), written once: 16 B read + 16 B write per amplitude, no memset, no atomics.
+struct MathInverseDesc {
+    int mode;
+    unsigned long long a_sub;   // ADD: a mod 2^64 (subtracted mod 2^nb);  ADD_MOD: a;  MUL_MOD: a^-1 mod N
+    unsigned long long N, barrett;  // barrett = floor(2^64 / N) (MUL_MOD, N < 2^32)
+    uint64_t ctrl_mask, reg_mask;
+    int n_regs;
+    int seg_off[17];            // register r is made of seg[seg_off[r] .. seg_off[r+1])
+    uint8_t nb[16];             // bits of register r
+    struct Seg {
+        uint8_t pos, len, shift;  // bits [pos, pos+len) of the index <-> bits [shift, shift+len) of the register's value
+    } seg[64];
+};
+void emulate_math_inverse(const Ctx& c, const double2* in, double2* out, uint64_t n_amps, const MathInverseDesc& d);
+
 // Pauli strings in physical-bit form: (P psi)[j] = phase * (-1)^{popcount(s & zmask)} psi[s], s = j ^ xmask, with
 // phase = coefficient * i^{nY} (reference: apply_term, simulator.hpp:538-550).
 struct PauliTerm {

@@ -415,3 +415,67 @@ def test_opt_in_kernel_paths_match_the_oracle(env):
                          env=dict(os.environ, **env), cwd=root)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert "opt-in paths OK" in out.stdout
+
+
+def _numpy_math(vec, n, regs, ctrl, f):
+    """new[pi(i)] += psi[i] (simulator.hpp:224-269) vectorised, 64-bit register arithmetic, sources added in index order"""
+    idx = np.arange(1 << n, dtype=np.int64)
+    cmask = sum(1 << c for c in ctrl)
+    ni = idx.copy()
+    for reg in regs:
+        x = np.zeros_like(idx)
+        for b, p in enumerate(reg):
+            x |= ((idx >> p) & 1) << b
+        y = f(x) & ((1 << len(reg)) - 1)
+        for b, p in enumerate(reg):
+            ni = (ni & ~(1 << p)) | (((y >> b) & 1) << p)
+    ni = np.where((idx & cmask) == cmask, ni, idx)
+    new = np.zeros_like(vec)
+    np.add.at(new, ni, vec)
+    return new
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["add", "addmod_near", "addmod_small_N", "mulmod", "mulmod_two_regs", "mulmod_not_coprime"])
+def test_emulate_math_wide_registers_closed_form_inverse(Backend, case):
+    """registers too wide to tabulate (> 20 bits): the closed-form inverse gather, bit-exact against a NumPy scatter — also
+    where the random state populates values outside the gate's domain (x >= N: several sources per destination), and the
+    atomic fallback when a is not invertible mod N"""
+    n = 24
+    rng = np.random.default_rng(17)
+    wf = rand_state(rng, n)
+    gpu = Backend(1)
+    for q in range(n):
+        gpu.allocate_qubit(q)
+    gpu.set_wavefunction(wf, list(range(n)))
+    scrambled = [3, 1, 2, 4, 5, 6, 7, 9, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22]  # 22 bits, three runs
+    if case == "add":
+        regs, ctrl, args = [scrambled], [23], ("emulate_math_addConstant", (-1234567,))
+        f = lambda x: x - 1234567
+    elif case == "addmod_near":
+        N = 4194301
+        regs, ctrl, args = [scrambled], [0], ("emulate_math_addConstantModN", (4000000, N))
+        f = lambda x: (x + 4000000) % N
+    elif case == "addmod_small_N":
+        N = 1500007
+        regs, ctrl, args = [list(range(1, 23))], [], ("emulate_math_addConstantModN", (77, N))
+        f = lambda x: (x + 77) % N
+    elif case == "mulmod":
+        N = 4194301
+        regs, ctrl, args = [list(range(2, 24))], [0, 1], ("emulate_math_multiplyByConstantModN", (1234577, N))
+        f = lambda x: (x * 1234577) % N
+    elif case == "mulmod_two_regs":
+        N = 2039
+        regs, ctrl, args = [list(range(0, 11)), list(range(12, 23))], [23], ("emulate_math_multiplyByConstantModN", (7, N))
+        f = lambda x: (x * 7) % N
+    else:
+        N = 4194300  # gcd(6, N) != 1: not a permutation, the scatter with atomics takes it
+        regs, ctrl, args = [list(range(1, 23))], [], ("emulate_math_multiplyByConstantModN", (6, N))
+        f = lambda x: (x * 6) % N
+    getattr(gpu, args[0])(*args[1], regs, ctrl)
+    got = np.asarray(gpu.cheat()[1])
+    want = _numpy_math(wf, n, regs, ctrl, f)
+    if case == "mulmod_not_coprime":
+        assert np.max(np.abs(got - want)) < 1e-12  # atomics: the order of the additions is not fixed
+    else:
+        assert np.array_equal(got, want), float(np.max(np.abs(got - want)))
