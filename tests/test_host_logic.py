@@ -353,3 +353,38 @@ def test_pauli_tile_planner_covers_every_term_once(lib):
     # a state smaller than a tile: one launch, every bit a tile bit
     launch, masks = plan_tiles(lib, [1, 6, 0], [0, 1, 7], 3)
     assert masks == [7] and launch == [0, 0, 0]
+
+
+_BLOCK_PLANNER_SCRIPT = r"""
+import ctypes, os, sys
+sys.path.insert(0, %r)
+from tests.test_host_logic import plan_tiles
+from projectq_b200 import _build
+lib = ctypes.CDLL(_build.LIB)
+n, B = 28, 20
+xm = [0] * (n - 1) + [1 << i for i in range(n)]
+zm = [(1 << i) | (1 << (i + 1)) for i in range(n - 1)] + [0] * n
+launch, masks = plan_tiles(lib, xm, zm, n)
+assert len(masks) == 3 and all(bin(m).count("1") == 11 for m in masks), masks
+inside = [m for m in masks if m >> B == 0]
+assert len(inside) == 2 and masks[:2] == inside, [hex(m) for m in masks]      # the sets below the block bits come first
+for x, l in zip(xm, launch):
+    assert 0 <= l < len(masks) and (x & ~masks[l]) == 0
+    if x and x >> B == 0:
+        assert masks[l] >> B == 0                                             # ... and take every term that fits below them
+print("block planner OK")
+"""
+
+
+def test_pauli_tile_planner_orders_sets_for_block_fusion():
+    """PQB_PAULI_BLOCK_BITS (opt-in fused execution): the tile-bit sets that lie below the block bits are planned first and
+    take every term whose X/Y support fits below them; the rest of the cover is unchanged (3 sets for the 28-qubit TFIM)"""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _BLOCK_PLANNER_SCRIPT % root], capture_output=True, text=True, timeout=120,
+                         env=dict(os.environ, PQB_PAULI_BLOCK_BITS="20"), cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "block planner OK" in out.stdout
