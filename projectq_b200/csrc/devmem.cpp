@@ -104,7 +104,13 @@ void GrowBuffer::ensure(size_t bytes, cudaStream_t stream) {
     if (vmm_) {
         const DriverApi& d = driver();
         if (bytes > va_size_) throw std::bad_alloc();
-        const size_t add = round_up(bytes - mapped_, gran_);
+        // Small states grow in one step: every mapping costs three driver calls (cuMemCreate / cuMemMap / cuMemSetAccess,
+        // ~1.5 ms together on B200), which dominated allocate_qubit for 20-qubit programs (6.8 ms of an 11 ms QFT-20 replay
+        // for the four mappings of 2, 2, 4, 8 MB).  Below kMinMapped the buffer is mapped up to kMinMapped at once.
+        constexpr size_t kMinMapped = size_t(64) << 20;  // 22 qubits
+        size_t want = bytes - mapped_;
+        if (bytes < kMinMapped && kMinMapped <= va_size_) want = kMinMapped - mapped_;
+        const size_t add = round_up(want, gran_);
         CUmemAllocationProp prop = alloc_prop(device_, exportable_);
         CUmemGenericAllocationHandle h = 0;
         if (d.memCreate(&h, add, &prop, 0) != CUDA_SUCCESS) {

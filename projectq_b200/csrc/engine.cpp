@@ -909,6 +909,12 @@ void Engine::measure_qubits(const uint32_t* ids, size_t n, uint8_t* out) {
         pick |= uint64_t(chosen) << lo;
         decided |= ((uint64_t(1) << m) - 1) << lo;
         top = lo;
+        // only the measured bits of the picked index are needed: once every measured position is decided the lower levels
+        // (one kernel and one host round trip each) cannot change the outcome
+        bool all_decided = true;
+        for (auto lp : lpos)
+            if (int(lp) < lo) all_decided = false;
+        if (all_decided) break;
     }
     (void)decided;
 
