@@ -175,8 +175,10 @@ constexpr int kTileTerms = 64;      // terms per launch
 // Everything the kernel needs is expressed in tile coordinates (bit i of a tile coordinate = index bit tile_pos[i]), so the
 // per-amplitude work is 32-bit: a term's sign (-1)^{popcount(s & zmask)} on the source index s = j ^ xmask factors into a
 // per-tile factor from the z bits outside the tile (s and j agree there; applied to the coefficient once per tile, in
-// shared memory) and a per-amplitude factor from the z bits inside the tile, taken on the source's tile coordinate.  Diagonal terms (xmask = 0) are split three ways: z entirely inside the tile -> one host-built table
-// w_in[tile coordinate] shared by all tiles; z entirely outside -> one scalar per tile; the rest are treated like any term.
+// shared memory), a constant (-1)^{popcount(xl & zl)} folded into the coefficient by the host, and a per-amplitude factor
+// (-1)^{popcount(t & zl)} on the OUTPUT tile coordinate t.  Diagonal terms (xmask = 0) are split three ways: z entirely
+// inside the tile -> one host-built table w_in[tile coordinate] shared by all tiles; z entirely outside -> one scalar per
+// tile; the rest are treated like any term.
 struct PauliTileArgs {
     double2 coef[kTileTerms];       // c_t * i^{nY}
     uint64_t z_out[kTileTerms];     // z bits outside the tile (index positions)
