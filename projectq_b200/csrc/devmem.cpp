@@ -6,6 +6,7 @@
 #include <unistd.h>
 
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -72,6 +73,20 @@ CUmemAllocationProp alloc_prop(int device, bool exportable) {
 
 size_t round_up(size_t x, size_t g) { return (x + g - 1) / g * g; }
 
+// Small mappings are parked instead of torn down: a ProjectQ program creates one Simulator per MainEngine, and reserving
+// the address range + mapping the first 64 MB costs ~2 ms of driver calls each time (measured on B200: engine construction
+// 1.7-3.7 ms, most of it here).  A destroyed single-GPU buffer that holds exactly its first mapping hands {address range,
+// chunk} to this per-process list (at most kMaxParked entries, 64 MB each); init() takes one back when the device matches.
+constexpr size_t kMinMapped = size_t(64) << 20;  // 22 qubits
+constexpr size_t kMaxParked = 4;
+struct Parked {
+    int device;
+    unsigned long long base, handle;
+    size_t va_size, gran, mapped;
+};
+std::mutex g_parked_mutex;
+std::vector<Parked> g_parked;
+
 }  // namespace
 
 void GrowBuffer::init(int device, bool exportable) {
@@ -81,6 +96,22 @@ void GrowBuffer::init(int device, bool exportable) {
     inited_ = true;
     const DriverApi& d = driver();
     if (!d.ok) return;  // plain cudaMalloc mode
+    if (!exportable_) {
+        std::lock_guard<std::mutex> lock(g_parked_mutex);
+        for (size_t i = 0; i < g_parked.size(); ++i) {
+            if (g_parked[i].device != device_) continue;
+            const Parked pk = g_parked[i];
+            g_parked.erase(g_parked.begin() + long(i));
+            base_ = pk.base;
+            va_size_ = pk.va_size;
+            gran_ = pk.gran;
+            mapped_ = pk.mapped;
+            chunks_.push_back({pk.handle, pk.mapped});
+            vmm_ = true;
+            ++generation_;
+            return;
+        }
+    }
     CUmemAllocationProp prop = alloc_prop(device_, exportable_);
     size_t gran = 0;
     if (d.memGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return;
@@ -107,7 +138,6 @@ void GrowBuffer::ensure(size_t bytes, cudaStream_t stream) {
         // Small states grow in one step: every mapping costs three driver calls (cuMemCreate / cuMemMap / cuMemSetAccess,
         // ~1.5 ms together on B200), which dominated allocate_qubit for 20-qubit programs (6.8 ms of an 11 ms QFT-20 replay
         // for the four mappings of 2, 2, 4, 8 MB).  Below kMinMapped the buffer is mapped up to kMinMapped at once.
-        constexpr size_t kMinMapped = size_t(64) << 20;  // 22 qubits
         size_t want = bytes - mapped_;
         if (bytes < kMinMapped && kMinMapped <= va_size_) want = kMinMapped - mapped_;
         const size_t add = round_up(want, gran_);
@@ -253,6 +283,19 @@ void PeerMapping::reset() {
 
 GrowBuffer::~GrowBuffer() {
     if (!inited_) return;
+    if (vmm_ && !exportable_ && base_ && !chunks_.empty()) {
+        shrink_to(1);  // back to the first mapping (waits for the device)
+        if (chunks_.size() == 1 && chunks_[0].size == mapped_ && mapped_ <= kMinMapped) {
+            std::lock_guard<std::mutex> lock(g_parked_mutex);
+            if (g_parked.size() < kMaxParked) {
+                g_parked.push_back({device_, base_, chunks_[0].handle, va_size_, gran_, mapped_});
+                chunks_.clear();
+                base_ = 0;
+                mapped_ = 0;
+                return;
+            }
+        }
+    }
     shrink_to(0);
     if (vmm_ && base_) driver().memAddressFree(base_, va_size_);
 }

@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "bits.h"
 #include "dist.h"
@@ -34,6 +36,23 @@ constexpr int kMinLocalBits = 8;         // sharded runs: qubits go to local bit
 // ---------------------------------------------------------------------------------------------------------------
 // construction
 // ---------------------------------------------------------------------------------------------------------------
+namespace {
+// The per-engine stream, events and small device / pinned scratch are recycled between engines of one process (a ProjectQ
+// program creates a Simulator per MainEngine; creating these cost 1-2 ms per engine, cudaMallocHost alone a good part of it).
+struct EngineKit {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    double* d_partials;
+    unsigned* d_pauli_sync;
+    double* d_scalars;
+    double* h_pinned;
+};
+constexpr size_t kMaxKits = 4;
+std::mutex g_kit_mutex;
+std::vector<EngineKit> g_kits;
+}  // namespace
+
 Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
     device_ = o.device;
     fusion_max_ = o.fusion_max_qubits <= 0 ? 0 : std::min(o.fusion_max_qubits, 5);  // 0 = choose per flush
@@ -52,15 +71,35 @@ Engine::Engine(uint32_t seed, const pqb_opts& o) : rng_(seed) {
     PQB_CHECK(cudaSetDevice(device_));
     // (cudaGetDeviceProperties takes milliseconds; small circuits create engines often)
     PQB_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
-    PQB_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    PQB_CHECK(cudaEventCreate(&ev0_));
-    PQB_CHECK(cudaEventCreate(&ev1_));
+    bool recycled = false;
+    {
+        std::lock_guard<std::mutex> lock(g_kit_mutex);
+        for (size_t i = 0; i < g_kits.size(); ++i) {
+            if (g_kits[i].device != device_) continue;
+            const EngineKit kit = g_kits[i];
+            g_kits.erase(g_kits.begin() + long(i));
+            stream_ = kit.stream;
+            ev0_ = kit.ev0;
+            ev1_ = kit.ev1;
+            d_partials_ = kit.d_partials;
+            d_pauli_sync_ = kit.d_pauli_sync;
+            d_scalars_ = kit.d_scalars;
+            h_pinned_ = kit.h_pinned;
+            recycled = true;
+            break;
+        }
+    }
+    if (!recycled) {
+        PQB_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        PQB_CHECK(cudaEventCreate(&ev0_));
+        PQB_CHECK(cudaEventCreate(&ev1_));
+        PQB_CHECK(cudaMalloc(&d_partials_, sizeof(double) * k::kReducePartials));
+        PQB_CHECK(cudaMalloc(&d_pauli_sync_, sizeof(unsigned) * k::kPauliSyncWords));
+        PQB_CHECK(cudaMalloc(&d_scalars_, sizeof(double) * kScalarDoubles));
+        PQB_CHECK(cudaMallocHost(&h_pinned_, sizeof(double) * kScalarDoubles));
+    }
     // only the state buffer reserves its address range now; the two scratch buffers do so on first use (ensure_scratch)
     state_->init(device_, /*exportable=*/world_ > 1);
-    PQB_CHECK(cudaMalloc(&d_partials_, sizeof(double) * k::kReducePartials));
-    PQB_CHECK(cudaMalloc(&d_pauli_sync_, sizeof(unsigned) * k::kPauliSyncWords));
-    PQB_CHECK(cudaMalloc(&d_scalars_, sizeof(double) * kScalarDoubles));
-    PQB_CHECK(cudaMallocHost(&h_pinned_, sizeof(double) * kScalarDoubles));
 
     if (world_ > 1) {
         if (!o.nccl_unique_id) throw ValueErr("pqb_create: nccl_unique_id is required when world_size > 1");
@@ -87,18 +126,28 @@ Engine::~Engine() {
     for (auto e : used_events_) cudaEventDestroy(e);
     for (auto e : free_events_) cudaEventDestroy(e);
     dist_.reset();
-    if (d_partials_) cudaFree(d_partials_);
-    if (d_pauli_sync_) cudaFree(d_pauli_sync_);
-    if (d_scalars_) cudaFree(d_scalars_);
-    if (h_pinned_) cudaFreeHost(h_pinned_);
     if (d_small_) cudaFree(d_small_);
     if (d_flush_) cudaFree(d_flush_);
-    if (ev0_) cudaEventDestroy(ev0_);
-    if (ev1_) cudaEventDestroy(ev1_);
     if (remap_e0_) cudaEventDestroy(remap_e0_);
     if (remap_e1_) cudaEventDestroy(remap_e1_);
-    for (auto& b : buf_) b.release();
-    if (stream_) cudaStreamDestroy(stream_);
+    // (the buffers park or release their memory in their own destructors, after this body)
+    bool kept = false;
+    if (stream_ && ev0_ && ev1_ && d_partials_ && d_pauli_sync_ && d_scalars_ && h_pinned_) {
+        std::lock_guard<std::mutex> lock(g_kit_mutex);
+        if (g_kits.size() < kMaxKits) {
+            g_kits.push_back({device_, stream_, ev0_, ev1_, d_partials_, d_pauli_sync_, d_scalars_, h_pinned_});
+            kept = true;
+        }
+    }
+    if (!kept) {
+        if (d_partials_) cudaFree(d_partials_);
+        if (d_pauli_sync_) cudaFree(d_pauli_sync_);
+        if (d_scalars_) cudaFree(d_scalars_);
+        if (h_pinned_) cudaFreeHost(h_pinned_);
+        if (ev0_) cudaEventDestroy(ev0_);
+        if (ev1_) cudaEventDestroy(ev1_);
+        if (stream_) cudaStreamDestroy(stream_);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
